@@ -1,0 +1,196 @@
+// common.cuh -- shared infrastructure of libcsr_cuda.so (sm_100a only).
+//
+// Context (device, stream, memory pool), per-thread error string, RAII device
+// buffers on the stream-ordered allocator, launch accounting and small device
+// helpers used by every kernel file.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "csrk.h"
+
+namespace csrk {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CSRK_CUDA(call)                                                          \
+    do {                                                                         \
+        cudaError_t _e = (call);                                                 \
+        if (_e != cudaSuccess)                                                   \
+            return ::csrk::cuda_fail(_e, #call, __FILE__, __LINE__);             \
+    } while (0)
+
+#define CSRK_TRY(call)                                                           \
+    do {                                                                         \
+        int _rc = (call);                                                        \
+        if (_rc != CSRK_OK)                                                      \
+            return _rc;                                                          \
+    } while (0)
+
+#define CSRK_ARG(cond, ...)                                                      \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            ::csrk::set_error(__VA_ARGS__);                                      \
+            return CSRK_EARG;                                                    \
+        }                                                                        \
+    } while (0)
+
+// ----------------------------------------------------------------- context
+struct Context {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;  // max dynamic shared memory per CTA (227 KB on B200)
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+Context &ctx();
+int ensure_init();  // CSRK_OK once csrk_init has run (auto-inits device 0 / $LOCAL_RANK)
+
+extern std::atomic<int64_t> g_launches;
+
+// every kernel launch goes through this so csrk_launch_count() is exact
+#define CSRK_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
+    do {                                                                         \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+        ::csrk::g_launches.fetch_add(1, std::memory_order_relaxed);              \
+        CSRK_CUDA(cudaGetLastError());                                           \
+    } while (0)
+
+// ------------------------------------------------- stream-ordered device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { reset(); }
+    int alloc(size_t nbytes, cudaStream_t stream);
+    int alloc_zero(size_t nbytes, cudaStream_t stream);
+    void reset();
+    void *release()
+    {
+        void *q = p;
+        p = nullptr;
+        bytes = 0;
+        return q;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+int dev_alloc(void **p, size_t bytes, cudaStream_t s);
+void dev_free(void *p, cudaStream_t s);
+
+// ------------------------------------------------------------------ matrix
+struct SpmvPlan;  // spmv.cu
+
+}  // namespace csrk
+
+// The opaque handle of csrk.h.  All pointers are device pointers owned here.
+struct csrk_matrix {
+    int32_t nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    void *rp = nullptr;     // int32[nrows+1] or int64[nrows+1]
+    int rp_is64 = 0;
+    int32_t *ci = nullptr;  // int32[nnz]
+    void *vs = nullptr;     // float[nnz] / double[nnz] / nullptr
+    int val_kind = 0;       // 0, 4, 8
+    int64_t stat_products = -1, stat_out_nnz = -1;
+    csrk::SpmvPlan *plan = nullptr;  // lazily built SpMV tile map
+    std::mutex mu;
+};
+
+namespace csrk {
+
+int matrix_alloc(csrk_matrix **out, int32_t nrows, int32_t ncols, int64_t nnz, int rp_is64, int val_kind,
+                 cudaStream_t s);
+void matrix_destroy(csrk_matrix *m, cudaStream_t s);
+void plan_destroy(SpmvPlan *p, cudaStream_t s);
+void plan_invalidate(csrk_matrix *m, cudaStream_t s);
+
+// ops implemented across the .cu files (all enqueue on `s`, no sync unless stated)
+int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s);
+int transpose_run(csrk_matrix *a, int with_values, csrk_matrix **out, cudaStream_t s);  // syncs internally
+int order_columns_run(csrk_matrix *h, cudaStream_t s);                                  // syncs internally
+int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s);        // syncs internally
+int filter_zeros_run(csrk_matrix *h, cudaStream_t s);                                   // syncs internally
+
+// ---------------------------------------------------------- device helpers
+__device__ __forceinline__ int64_t ld_rp(const void *rp, int is64, int64_t i)
+{
+    return is64 ? reinterpret_cast<const int64_t *>(rp)[i] : (int64_t) reinterpret_cast<const int32_t *>(rp)[i];
+}
+
+__device__ __forceinline__ double ld_val(const void *vs, int kind, int64_t i)
+{
+    if (kind == 8)
+        return reinterpret_cast<const double *>(vs)[i];
+    if (kind == 4)
+        return (double)reinterpret_cast<const float *>(vs)[i];
+    return 1.0;
+}
+
+// streaming 128-bit loads: read-only path, do not allocate in L1 (keep L1 for gathers)
+__device__ __forceinline__ int4 ld_stream_int4(const void *ptr)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(ptr));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream_float4(const void *ptr)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(ptr));
+    return r;
+}
+__device__ __forceinline__ double2 ld_stream_double2(const void *ptr)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(ptr));
+    return r;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// first index i in [lo, hi) with rp[i] >= key (hi if none)
+template <typename RPT> __device__ __forceinline__ int64_t lower_bound_rp(const RPT *rp, int64_t lo, int64_t hi, int64_t key)
+{
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)rp[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace csrk

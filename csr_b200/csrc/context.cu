@@ -1,0 +1,472 @@
+// context.cu -- library context, error reporting and the handle lifecycle
+// (to_handle / from_handle / release_handle of the kernel contract:
+// csr/kernels/numba/__init__.py:16-44, precedent csr/kernels/mkl/handle.py:46-148).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace csrk {
+
+static thread_local std::string t_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation)
+        return CSRK_ENOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return CSRK_ENODEV;
+    return CSRK_ECUDA;
+}
+
+Context &ctx()
+{
+    static Context c;
+    return c;
+}
+
+static int init_locked(Context &c, int device)
+{
+    if (c.inited) {
+        CSRK_ARG(device < 0 || device == c.device, "csrk_init(%d): library already bound to device %d", device, c.device);
+        return CSRK_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no usable CUDA device (%s); libcsr_cuda has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        (void)cudaGetLastError();
+        return CSRK_ENODEV;
+    }
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % ndev : 0;
+    }
+    CSRK_ARG(device < ndev, "csrk_init(%d): only %d device(s)", device, ndev);
+    CSRK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CSRK_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) {
+        set_error("device %d is sm_%d%d; libcsr_cuda is built for sm_100a only", device, p.major, p.minor);
+        return CSRK_ENODEV;
+    }
+    c.device = device;
+    c.sm_count = p.multiProcessorCount;
+    c.cc_major = p.major;
+    c.cc_minor = p.minor;
+    c.smem_optin = p.sharedMemPerBlockOptin;
+    CSRK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    // keep freed blocks in the pool: handle churn (to_handle per call, csr.py:582) must not hit cudaMalloc
+    cudaMemPool_t pool;
+    CSRK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CSRK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c.inited = true;
+    return CSRK_OK;
+}
+
+int ensure_init()
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    CSRK_TRY(init_locked(c, -1));
+    // the runtime's current device is per host thread
+    CSRK_CUDA(cudaSetDevice(c.device));
+    return CSRK_OK;
+}
+
+int dev_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    *p = nullptr;
+    if (bytes == 0)
+        bytes = 16;  // never hand out NULL for an empty array: kernels may form (unused) pointers
+    cudaError_t e = cudaMallocAsync(p, bytes, s);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? CSRK_ENOMEM : CSRK_ECUDA;
+    }
+    return CSRK_OK;
+}
+
+void dev_free(void *p, cudaStream_t s)
+{
+    if (p)
+        (void)cudaFreeAsync(p, s);
+}
+
+int DevBuf::alloc(size_t nbytes, cudaStream_t stream)
+{
+    reset();
+    s = stream;
+    CSRK_TRY(dev_alloc(&p, nbytes, stream));
+    bytes = nbytes;
+    return CSRK_OK;
+}
+
+int DevBuf::alloc_zero(size_t nbytes, cudaStream_t stream)
+{
+    CSRK_TRY(alloc(nbytes, stream));
+    CSRK_CUDA(cudaMemsetAsync(p, 0, nbytes ? nbytes : 16, stream));
+    return CSRK_OK;
+}
+
+void DevBuf::reset()
+{
+    if (p)
+        dev_free(p, s);
+    p = nullptr;
+    bytes = 0;
+}
+
+int matrix_alloc(csrk_matrix **out, int32_t nrows, int32_t ncols, int64_t nnz, int rp_is64, int val_kind, cudaStream_t s)
+{
+    *out = nullptr;
+    csrk_matrix *m = new (std::nothrow) csrk_matrix();
+    if (!m) {
+        set_error("host allocation failed");
+        return CSRK_ENOMEM;
+    }
+    m->nrows = nrows;
+    m->ncols = ncols;
+    m->nnz = nnz;
+    m->rp_is64 = rp_is64;
+    m->val_kind = val_kind;
+    int rc = dev_alloc(&m->rp, ((size_t)nrows + 1) * (rp_is64 ? 8 : 4), s);
+    if (rc == CSRK_OK)
+        rc = dev_alloc((void **)&m->ci, (size_t)nnz * 4, s);
+    if (rc == CSRK_OK && val_kind)
+        rc = dev_alloc(&m->vs, (size_t)nnz * val_kind, s);
+    if (rc != CSRK_OK) {
+        matrix_destroy(m, s);
+        return rc;
+    }
+    *out = m;
+    return CSRK_OK;
+}
+
+void matrix_destroy(csrk_matrix *m, cudaStream_t s)
+{
+    if (!m)
+        return;
+    dev_free(m->rp, s);
+    dev_free(m->ci, s);
+    dev_free(m->vs, s);
+    plan_destroy(m->plan, s);
+    delete m;
+}
+
+void plan_invalidate(csrk_matrix *m, cudaStream_t s)
+{
+    std::lock_guard<std::mutex> g(m->mu);
+    plan_destroy(m->plan, s);
+    m->plan = nullptr;
+}
+
+static int check_shape(int32_t nrows, int32_t ncols, int64_t nnz, int rp_is64, int val_kind)
+{
+    CSRK_ARG(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative dimension (nrows=%d ncols=%d nnz=%lld)", nrows, ncols,
+             (long long)nnz);
+    CSRK_ARG(val_kind == 0 || val_kind == 4 || val_kind == 8, "val_kind must be 0, 4 or 8 (got %d)", val_kind);
+    CSRK_ARG(rp_is64 || nnz <= INT32_MAX, "int32 rowptrs cannot address %lld entries", (long long)nnz);
+    return CSRK_OK;
+}
+
+template <typename RPT> __global__ void k_rebase(const RPT *src, RPT *dst, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = src[i] - src[0];
+}
+
+}  // namespace csrk
+
+using namespace csrk;
+
+extern "C" {
+
+int csrk_version(void) { return 100; }
+
+const char *csrk_last_error(void) { return t_error.c_str(); }
+
+int csrk_init(int device)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    return init_locked(c, device);
+}
+
+int csrk_shutdown(void)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> g(c.mu);
+    if (!c.inited)
+        return CSRK_OK;
+    CSRK_CUDA(cudaSetDevice(c.device));
+    CSRK_CUDA(cudaStreamSynchronize(c.stream));
+    CSRK_CUDA(cudaStreamDestroy(c.stream));
+    c.stream = nullptr;
+    c.inited = false;
+    return CSRK_OK;
+}
+
+int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *cc_major, int *cc_minor)
+{
+    CSRK_TRY(ensure_init());
+    size_t f = 0, t = 0;
+    CSRK_CUDA(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = ctx().sm_count;
+    if (mem_total) *mem_total = (int64_t)t;
+    if (mem_free) *mem_free = (int64_t)f;
+    if (cc_major) *cc_major = ctx().cc_major;
+    if (cc_minor) *cc_minor = ctx().cc_minor;
+    return CSRK_OK;
+}
+
+int64_t csrk_launch_count(void) { return g_launches.load(); }
+
+int csrk_synchronize(void)
+{
+    CSRK_TRY(ensure_init());
+    CSRK_CUDA(cudaStreamSynchronize(ctx().stream));
+    return CSRK_OK;
+}
+
+static int create_impl(int32_t nrows, int32_t ncols, int64_t nnz, const void *rowptrs, int rp_is64,
+                       const int32_t *colinds, const void *values, int val_kind, cudaStream_t s, cudaMemcpyKind kind,
+                       csrk_h *out)
+{
+    CSRK_ARG(out != nullptr, "out handle pointer is NULL");
+    *out = nullptr;
+    CSRK_TRY(check_shape(nrows, ncols, nnz, rp_is64, val_kind));
+    CSRK_ARG(rowptrs != nullptr, "rowptrs is NULL");
+    CSRK_ARG(nnz == 0 || colinds != nullptr, "colinds is NULL");
+    CSRK_ARG(val_kind == 0 || nnz == 0 || values != nullptr, "values is NULL but val_kind=%d", val_kind);
+    csrk_matrix *m = nullptr;
+    CSRK_TRY(matrix_alloc(&m, nrows, ncols, nnz, rp_is64, val_kind, s));
+    cudaError_t e = cudaMemcpyAsync(m->rp, rowptrs, ((size_t)nrows + 1) * (rp_is64 ? 8 : 4), kind, s);
+    if (e == cudaSuccess && nnz)
+        e = cudaMemcpyAsync(m->ci, colinds, (size_t)nnz * 4, kind, s);
+    if (e == cudaSuccess && nnz && val_kind)
+        e = cudaMemcpyAsync(m->vs, values, (size_t)nnz * val_kind, kind, s);
+    if (e == cudaSuccess && kind == cudaMemcpyHostToDevice)
+        e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        matrix_destroy(m, s);
+        return cuda_fail(e, "upload", __FILE__, __LINE__);
+    }
+    *out = m;
+    return CSRK_OK;
+}
+
+int csrk_create(int32_t nrows, int32_t ncols, int64_t nnz, const void *rowptrs, int rp_is64, const int32_t *colinds,
+                const void *values, int val_kind, csrk_h *out)
+{
+    CSRK_TRY(ensure_init());
+    return create_impl(nrows, ncols, nnz, rowptrs, rp_is64, colinds, values, val_kind, ctx().stream,
+                       cudaMemcpyHostToDevice, out);
+}
+
+int csrk_create_dev(int32_t nrows, int32_t ncols, int64_t nnz, const void *d_rowptrs, int rp_is64,
+                    const int32_t *d_colinds, const void *d_values, int val_kind, void *stream, csrk_h *out)
+{
+    CSRK_TRY(ensure_init());
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx().stream;
+    return create_impl(nrows, ncols, nnz, d_rowptrs, rp_is64, d_colinds, d_values, val_kind, s,
+                       cudaMemcpyDeviceToDevice, out);
+}
+
+int csrk_free(csrk_h h)
+{
+    if (!h)
+        return CSRK_OK;
+    CSRK_TRY(ensure_init());
+    matrix_destroy(h, ctx().stream);
+    return CSRK_OK;
+}
+
+int csrk_dims(csrk_h h, int32_t *nrows, int32_t *ncols, int64_t *nnz, int *rp_is64, int *val_kind)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    if (nrows) *nrows = h->nrows;
+    if (ncols) *ncols = h->ncols;
+    if (nnz) *nnz = h->nnz;
+    if (rp_is64) *rp_is64 = h->rp_is64;
+    if (val_kind) *val_kind = h->val_kind;
+    return CSRK_OK;
+}
+
+int csrk_export(csrk_h h, void *rowptrs, int32_t *colinds, void *values)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_ARG(rowptrs != nullptr, "rowptrs is NULL");
+    CSRK_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    CSRK_CUDA(cudaMemcpyAsync(rowptrs, h->rp, ((size_t)h->nrows + 1) * (h->rp_is64 ? 8 : 4), cudaMemcpyDeviceToHost, s));
+    if (h->nnz) {
+        CSRK_ARG(colinds != nullptr, "colinds is NULL");
+        CSRK_CUDA(cudaMemcpyAsync(colinds, h->ci, (size_t)h->nnz * 4, cudaMemcpyDeviceToHost, s));
+        if (h->val_kind) {
+            CSRK_ARG(values != nullptr, "values is NULL");
+            CSRK_CUDA(cudaMemcpyAsync(values, h->vs, (size_t)h->nnz * h->val_kind, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    return CSRK_OK;
+}
+
+int csrk_device_ptrs(csrk_h h, void **d_rowptrs, int32_t **d_colinds, void **d_values)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    if (d_rowptrs) *d_rowptrs = h->rp;
+    if (d_colinds) *d_colinds = h->ci;
+    if (d_values) *d_values = h->vs;
+    return CSRK_OK;
+}
+
+int csrk_subset_rows(csrk_h h, int32_t begin, int32_t end, csrk_h *out)
+{
+    CSRK_ARG(h != nullptr && out != nullptr, "NULL handle");
+    CSRK_ARG(0 <= begin && begin <= end && end <= h->nrows, "row range [%d,%d) outside [0,%d]", begin, end, h->nrows);
+    CSRK_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    *out = nullptr;
+    // the two bounding row pointers decide the slice of colinds/values
+    int64_t st = 0, ed = 0;
+    const size_t w = h->rp_is64 ? 8 : 4;
+    int64_t tmp[2] = {0, 0};
+    CSRK_CUDA(cudaMemcpyAsync(&tmp[0], (const char *)h->rp + (size_t)begin * w, w, cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaMemcpyAsync(&tmp[1], (const char *)h->rp + (size_t)end * w, w, cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    if (h->rp_is64) {
+        st = tmp[0];
+        ed = tmp[1];
+    } else {
+        st = *(int32_t *)&tmp[0];
+        ed = *(int32_t *)&tmp[1];
+    }
+    const int64_t nnz = ed - st;
+    const int32_t nr = end - begin;
+    csrk_matrix *m = nullptr;
+    // keep the parent's rowptr width (subset_rows slices the same array: structure.py:72-74)
+    CSRK_TRY(matrix_alloc(&m, nr, h->ncols, nnz, h->rp_is64, h->val_kind, s));
+    const unsigned grid = (unsigned)div_up((int64_t)nr + 1, 256);
+    cudaError_t e = cudaSuccess;
+    if (h->rp_is64)
+        k_rebase<int64_t><<<grid, 256, 0, s>>>((const int64_t *)h->rp + begin, (int64_t *)m->rp, (int64_t)nr + 1);
+    else
+        k_rebase<int32_t><<<grid, 256, 0, s>>>((const int32_t *)h->rp + begin, (int32_t *)m->rp, (int64_t)nr + 1);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && nnz)
+        e = cudaMemcpyAsync(m->ci, h->ci + st, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && nnz && h->val_kind)
+        e = cudaMemcpyAsync(m->vs, (const char *)h->vs + (size_t)st * h->val_kind, (size_t)nnz * h->val_kind,
+                            cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        matrix_destroy(m, s);
+        return cuda_fail(e, "subset_rows", __FILE__, __LINE__);
+    }
+    *out = m;
+    return CSRK_OK;
+}
+
+int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stream)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_ARG(x_kind == 4 || x_kind == 8, "x_kind must be 4 or 8 (got %d)", x_kind);
+    CSRK_ARG(h->ncols == 0 || d_x != nullptr, "x is NULL");
+    CSRK_ARG(h->nrows == 0 || d_y != nullptr, "y is NULL");
+    CSRK_TRY(ensure_init());
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx().stream;
+    return spmv_run(h, d_x, x_kind, d_y, s);
+}
+
+int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_ARG(x_kind == 4 || x_kind == 8, "x_kind must be 4 or 8 (got %d)", x_kind);
+    CSRK_ARG(h->ncols == 0 || x != nullptr, "x is NULL");
+    CSRK_ARG(h->nrows == 0 || y != nullptr, "y is NULL");
+    CSRK_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    DevBuf dx, dy;
+    CSRK_TRY(dx.alloc((size_t)h->ncols * x_kind, s));
+    CSRK_TRY(dy.alloc((size_t)h->nrows * 8, s));
+    if (h->ncols)
+        CSRK_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)h->ncols * x_kind, cudaMemcpyHostToDevice, s));
+    CSRK_TRY(spmv_run(h, dx.p, x_kind, dy.as<double>(), s));
+    if (h->nrows)
+        CSRK_CUDA(cudaMemcpyAsync(y, dy.p, (size_t)h->nrows * 8, cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    return CSRK_OK;
+}
+
+int csrk_spgemm(csrk_h a, csrk_h b, csrk_h *c)
+{
+    CSRK_ARG(a && b && c, "NULL handle");
+    CSRK_ARG(a->ncols == b->nrows, "mult_ab: a.ncols (%d) != b.nrows (%d)", a->ncols, b->nrows);
+    CSRK_TRY(ensure_init());
+    return spgemm_run(a, b, c, ctx().stream);
+}
+
+int csrk_spgemm_abt(csrk_h a, csrk_h b, csrk_h *c)
+{
+    CSRK_ARG(a && b && c, "NULL handle");
+    CSRK_ARG(a->ncols == b->ncols, "mult_abt: a.ncols (%d) != b.ncols (%d)", a->ncols, b->ncols);
+    CSRK_TRY(ensure_init());
+    cudaStream_t s = ctx().stream;
+    // multiply.py:56-57: bt = b.transpose(); mult_ab(a, bt)
+    csrk_matrix *bt = nullptr;
+    CSRK_TRY(transpose_run(b, 1, &bt, s));
+    int rc = spgemm_run(a, bt, c, s);
+    matrix_destroy(bt, s);
+    return rc;
+}
+
+int csrk_spgemm_stats(csrk_h c, int64_t *products, int64_t *out_nnz)
+{
+    CSRK_ARG(c != nullptr, "NULL handle");
+    if (products) *products = c->stat_products;
+    if (out_nnz) *out_nnz = c->stat_out_nnz;
+    return CSRK_OK;
+}
+
+int csrk_transpose(csrk_h a, int with_values, csrk_h *at)
+{
+    CSRK_ARG(a && at, "NULL handle");
+    CSRK_TRY(ensure_init());
+    return transpose_run(a, with_values, at, ctx().stream);
+}
+
+int csrk_order_columns(csrk_h h)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_TRY(ensure_init());
+    return order_columns_run(h, ctx().stream);
+}
+
+int csrk_filter_zeros(csrk_h h)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_TRY(ensure_init());
+    return filter_zeros_run(h, ctx().stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,322 @@
+// spmv.cu -- mult_vec (csr/kernels/numba/__init__.py:55-67) for sm_100a.
+//
+//   y[r] = sum_{i in row r} x[colinds[i]] * (values[i] or 1),   y float64.
+//
+// Work decomposition ("nnz-balanced row binning"): the nnz axis is cut into
+// tiles of SPMV_TILE entries; a tile map built once per handle stores, for each
+// tile, the first row that STARTS inside it (binary search on rowptrs).  One CTA
+// owns one tile, so every CTA streams the same number of bytes no matter how
+// skewed the row lengths are (a 1M-entry row is simply 244 tiles).
+//
+// Inside a tile
+//   phase 1  all threads stream colinds/values with 128-bit no-L1-allocate loads,
+//            gather x through the read-only path and park the products in shared
+//            memory (product type = numba's promotion: f4*f4 -> f4, else f8);
+//   phase 2  rows that start in the tile are reduced from shared memory in
+//            float64: scalar-per-row for short rows, vector(warp)-per-row with a
+//            shuffle reduction for long ones; the head of the tile that belongs
+//            to a row begun in an earlier tile is block-reduced into carry[tile].
+// A tiny fix-up kernel adds the carries of multi-tile rows in tile order, so the
+// result is deterministic (no float atomics anywhere).
+//
+// Algorithmic HBM bytes per nnz (f4 values, f4 x, int32 rowptrs):
+//   4 (colind) + 4 (value) + (nrows+1)*4/nnz + ncols*4/nnz + nrows*8/nnz  ~ 8.16 B at cfg2.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace csrk {
+
+constexpr int SPMV_BLOCK = 256;
+constexpr int SPMV_ITEMS = 16;
+constexpr int SPMV_TILE = SPMV_BLOCK * SPMV_ITEMS;  // 4096 nnz per CTA
+constexpr int SPMV_LONG = 48;                       // rows longer than this inside a tile go to a warp
+constexpr int SPMV_QCAP = SPMV_TILE / SPMV_LONG + 2;
+
+struct SpmvPlan {
+    int64_t ntiles = 0;
+    int32_t *tile_row = nullptr;  // [ntiles+1] first row with rowptr >= tile base; [ntiles] = nrows
+};
+
+void plan_destroy(SpmvPlan *p, cudaStream_t s)
+{
+    if (!p)
+        return;
+    dev_free(p->tile_row, s);
+    delete p;
+}
+
+struct NoVal {};
+
+template <typename VT, typename XT> struct Prod {
+    using type = double;
+};
+template <> struct Prod<float, float> {
+    using type = float;
+};
+
+template <typename RPT>
+__global__ void k_spmv_plan(const RPT *__restrict__ rp, int32_t nrows, int64_t ntiles, int32_t *__restrict__ tile_row)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles)
+        return;
+    if (t == ntiles) {
+        tile_row[t] = nrows;
+        return;
+    }
+    tile_row[t] = (int32_t)lower_bound_rp(rp, 0, (int64_t)nrows + 1, t * SPMV_TILE);
+}
+
+__global__ void k_zero_f64(double *y, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        y[i] = 0.0;
+}
+
+template <typename VT> struct ValLoad4 {
+    // four consecutive values starting at element index e (multiple of 4), as doubles or floats
+    __device__ static __forceinline__ void load(const VT *vs, int64_t e, VT (&v)[4]);
+};
+template <> __device__ __forceinline__ void ValLoad4<float>::load(const float *vs, int64_t e, float (&v)[4])
+{
+    float4 f = ld_stream_float4(vs + e);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+template <> __device__ __forceinline__ void ValLoad4<double>::load(const double *vs, int64_t e, double (&v)[4])
+{
+    double2 a = ld_stream_double2(vs + e), b = ld_stream_double2(vs + e + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename RPT, typename VT, typename XT>
+__global__ void __launch_bounds__(SPMV_BLOCK)
+k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_t *__restrict__ ci,
+            const VT *__restrict__ vs, const XT *__restrict__ x, double *__restrict__ y,
+            const int32_t *__restrict__ tile_row, double *__restrict__ carry)
+{
+    constexpr bool HASV = !std::is_same<VT, NoVal>::value;
+    using RV = typename std::conditional<HASV, VT, double>::type;  // real value type
+    using PT = typename Prod<RV, XT>::type;
+    __shared__ __align__(16) PT prod[SPMV_TILE];
+    __shared__ double wsum[SPMV_BLOCK / 32];
+    __shared__ int q_row[SPMV_QCAP];
+    __shared__ int q_n;
+
+    const int tid = threadIdx.x;
+    const int64_t t = blockIdx.x;
+    const int64_t base = t * SPMV_TILE;
+    const int cnt = (int)min((int64_t)SPMV_TILE, nnz - base);
+    if (tid == 0)
+        q_n = 0;
+
+    // ---- phase 1: stream + gather + multiply
+    if (cnt == SPMV_TILE) {
+        int4 c[SPMV_ITEMS / 4];
+        RV v[SPMV_ITEMS / 4][4];
+#pragma unroll
+        for (int k = 0; k < SPMV_ITEMS / 4; k++) {
+            const int64_t e = base + 4 * (k * SPMV_BLOCK + tid);
+            c[k] = ld_stream_int4(ci + e);
+            if constexpr (HASV)
+                ValLoad4<RV>::load(reinterpret_cast<const RV *>(vs), e, v[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < SPMV_ITEMS / 4; k++) {
+            XT x0 = __ldg(x + c[k].x), x1 = __ldg(x + c[k].y), x2 = __ldg(x + c[k].z), x3 = __ldg(x + c[k].w);
+            PT p0, p1, p2, p3;
+            if constexpr (HASV) {
+                p0 = (PT)x0 * (PT)v[k][0];
+                p1 = (PT)x1 * (PT)v[k][1];
+                p2 = (PT)x2 * (PT)v[k][2];
+                p3 = (PT)x3 * (PT)v[k][3];
+            } else {
+                p0 = (PT)x0; p1 = (PT)x1; p2 = (PT)x2; p3 = (PT)x3;
+            }
+            PT *dst = prod + 4 * (k * SPMV_BLOCK + tid);
+            if constexpr (sizeof(PT) == 4) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(p0, p1, p2, p3);
+            } else {
+                *reinterpret_cast<double2 *>(dst) = make_double2(p0, p1);
+                *reinterpret_cast<double2 *>(dst + 2) = make_double2(p2, p3);
+            }
+        }
+    } else {
+        for (int i = tid; i < cnt; i += SPMV_BLOCK) {
+            const int64_t e = base + i;
+            XT xv = __ldg(x + ci[e]);
+            if constexpr (HASV)
+                prod[i] = (PT)xv * (PT) reinterpret_cast<const RV *>(vs)[e];
+            else
+                prod[i] = (PT)xv;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: segmented reduction in float64
+    const int32_t rlo = tile_row[t], rhi = tile_row[t + 1];
+    const int64_t tend = base + cnt;
+    // head of the tile that continues a row begun earlier (rp[rlo] is valid: rlo <= nrows)
+    const int lead = (int)(min((int64_t)rp[rlo], tend) - base);
+    if (lead > 0) {
+        double s = 0.0;
+        for (int i = tid; i < lead; i += SPMV_BLOCK)
+            s += (double)prod[i];
+        s = warp_sum(s);
+        if ((tid & 31) == 0)
+            wsum[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < SPMV_BLOCK / 32; w++)
+                tot += wsum[w];
+            carry[t] = tot;
+        }
+    } else if (tid == 0) {
+        carry[t] = 0.0;
+    }
+
+    // scalar-per-row for short rows; long rows are queued for the warps
+    for (int32_t r = rlo + tid; r < rhi; r += SPMV_BLOCK) {
+        const int s0 = (int)((int64_t)rp[r] - base);
+        const int e0 = (int)(min((int64_t)rp[r + 1], tend) - base);
+        if (e0 - s0 > SPMV_LONG) {
+            int slot = atomicAdd(&q_n, 1);
+            q_row[slot] = r;
+        } else {
+            double s = 0.0;
+            for (int i = s0; i < e0; i++)
+                s += (double)prod[i];
+            y[r] = s;  // complete row, or the head piece of a row that continues (carries are added later)
+        }
+    }
+    __syncthreads();
+    const int nq = q_n;
+    for (int q = tid >> 5; q < nq; q += SPMV_BLOCK / 32) {
+        const int32_t r = q_row[q];
+        const int s0 = (int)((int64_t)rp[r] - base);
+        const int e0 = (int)(min((int64_t)rp[r + 1], tend) - base);
+        double s = 0.0;
+        for (int i = s0 + (tid & 31); i < e0; i += 32)
+            s += (double)prod[i];
+        s = warp_sum(s);
+        if ((tid & 31) == 0)
+            y[r] = s;
+    }
+}
+
+// One thread per tile t >= 1.  If tile t is the FIRST continuation tile of the row
+// that spills into it, add that row's carries in tile order: deterministic.
+template <typename RPT>
+__global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict__ rp,
+                             const int32_t *__restrict__ tile_row, const double *__restrict__ carry,
+                             double *__restrict__ y)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (t >= ntiles)
+        return;
+    const int64_t base = t * SPMV_TILE;
+    const int32_t rlo = tile_row[t];
+    if ((int64_t)rp[rlo] <= base)
+        return;                    // no head piece
+    const int32_t row = rlo - 1;   // the row spanning `base`
+    const int64_t rs = (int64_t)rp[row];
+    if (rs / SPMV_TILE != t - 1)
+        return;                    // an earlier tile is this row's first continuation
+    const int64_t re = (int64_t)rp[row + 1];
+    const int64_t tlast = (re - 1) / SPMV_TILE;
+    double tot = 0.0;
+    for (int64_t u = t; u <= tlast; u++)
+        tot += carry[u];
+    y[row] += tot;
+}
+
+static int ensure_plan(csrk_matrix *h, cudaStream_t s, SpmvPlan **out)
+{
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->plan) {
+        SpmvPlan *p = new (std::nothrow) SpmvPlan();
+        if (!p) {
+            set_error("host allocation failed");
+            return CSRK_ENOMEM;
+        }
+        p->ntiles = div_up(h->nnz, SPMV_TILE);
+        int rc = dev_alloc((void **)&p->tile_row, sizeof(int32_t) * (size_t)(p->ntiles + 1), s);
+        if (rc != CSRK_OK) {
+            delete p;
+            return rc;
+        }
+        const unsigned grid = (unsigned)div_up(p->ntiles + 1, 256);
+        if (h->rp_is64)
+            k_spmv_plan<int64_t><<<grid, 256, 0, s>>>((const int64_t *)h->rp, h->nrows, p->ntiles, p->tile_row);
+        else
+            k_spmv_plan<int32_t><<<grid, 256, 0, s>>>((const int32_t *)h->rp, h->nrows, p->ntiles, p->tile_row);
+        g_launches.fetch_add(1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            plan_destroy(p, s);
+            return cuda_fail(e, "k_spmv_plan", __FILE__, __LINE__);
+        }
+        // the plan may be consumed on another stream (csrk_spmv_dev): make it visible first
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            plan_destroy(p, s);
+            return cuda_fail(e, "plan sync", __FILE__, __LINE__);
+        }
+        h->plan = p;
+    }
+    *out = h->plan;
+    return CSRK_OK;
+}
+
+template <typename RPT, typename VT, typename XT>
+static int launch_spmv(csrk_matrix *h, SpmvPlan *p, const void *d_x, double *d_y, double *carry, cudaStream_t s)
+{
+    CSRK_LAUNCH((k_spmv_tile<RPT, VT, XT>), (unsigned)p->ntiles, SPMV_BLOCK, 0, s, h->nrows, h->nnz,
+                (const RPT *)h->rp, h->ci, (const VT *)h->vs, (const XT *)d_x, d_y, p->tile_row, carry);
+    if (p->ntiles > 1)
+        CSRK_LAUNCH((k_spmv_fixup<RPT>), (unsigned)div_up(p->ntiles - 1, 256), 256, 0, s, p->ntiles, h->nnz,
+                    (const RPT *)h->rp, p->tile_row, carry, d_y);
+    return CSRK_OK;
+}
+
+template <typename RPT, typename VT>
+static int launch_spmv_x(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kind, double *d_y, double *carry,
+                         cudaStream_t s)
+{
+    if (x_kind == 4)
+        return launch_spmv<RPT, VT, float>(h, p, d_x, d_y, carry, s);
+    return launch_spmv<RPT, VT, double>(h, p, d_x, d_y, carry, s);
+}
+
+template <typename RPT>
+static int launch_spmv_v(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kind, double *d_y, double *carry,
+                         cudaStream_t s)
+{
+    switch (h->val_kind) {
+    case 4: return launch_spmv_x<RPT, float>(h, p, d_x, x_kind, d_y, carry, s);
+    case 8: return launch_spmv_x<RPT, double>(h, p, d_x, x_kind, d_y, carry, s);
+    default: return launch_spmv_x<RPT, NoVal>(h, p, d_x, x_kind, d_y, carry, s);
+    }
+}
+
+int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s)
+{
+    if (h->nrows == 0)
+        return CSRK_OK;
+    if (h->nnz == 0) {
+        CSRK_LAUNCH(k_zero_f64, (unsigned)div_up(h->nrows, 256), 256, 0, s, d_y, (int64_t)h->nrows);
+        return CSRK_OK;
+    }
+    SpmvPlan *p = nullptr;
+    CSRK_TRY(ensure_plan(h, ctx().stream, &p));
+    DevBuf carry;
+    CSRK_TRY(carry.alloc(sizeof(double) * (size_t)p->ntiles, s));
+    if (h->rp_is64)
+        return launch_spmv_v<int64_t>(h, p, d_x, x_kind, d_y, carry.as<double>(), s);
+    return launch_spmv_v<int32_t>(h, p, d_x, x_kind, d_y, carry.as<double>(), s);
+}
+
+}  // namespace csrk

@@ -1,0 +1,331 @@
+// transpose.cu -- stable CSR->CSC (csr/structure.py:172-247) and order_columns
+// (csr/kernels/numba/__init__.py:47-52 -> structure.py:156-169) for sm_100a.
+//
+// The reference transpose is a counting sort by column whose scatter is STABLE
+// (structure.py:191-197: entries of an output row appear in source order).  An
+// atomic-cursor scatter is not, so the device version is a hand-written stable
+// LSD radix sort of (column key, source row, value) with 8-bit digits:
+//   per pass   k_radix_hist     per-tile digit histogram        (reads 4 B/nnz)
+//              exclusive_scan   digit-major (digit, tile) scan  (tiny)
+//              k_radix_scatter  stable rank + scatter           (reads+writes 8+V B/nnz)
+// Stability inside a tile comes from processing 32 consecutive entries per warp
+// step, ranking equal digits by lane with __match_any_sync, per-warp digit
+// counters, and an exclusive prefix over the warps of the CTA.
+//
+// order_columns is the same machinery applied twice: (A^T)^T with both counting
+// sorts stable leaves every row sorted by column with equal columns in their
+// original relative order -- exactly what the reference's bubble sort produces.
+#include <type_traits>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace csrk {
+
+constexpr int RS_BLOCK = 256;
+constexpr int RS_WARPS = RS_BLOCK / 32;
+constexpr int RS_STEPS = 16;
+constexpr int RS_TILE = RS_BLOCK * RS_STEPS;  // 4096 entries per CTA
+constexpr int RS_WARP_ITEMS = 32 * RS_STEPS;
+
+struct NoPayload {};
+
+__global__ void __launch_bounds__(RS_BLOCK)
+k_radix_hist(const int32_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ tile_hist, int64_t ntiles)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RS_STEPS; k++) {
+        int64_t i = base + (int64_t)k * RS_BLOCK + threadIdx.x;
+        if (i < n)
+            atomicAdd(&h[(keys[i] >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    tile_hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(RS_BLOCK)
+k_radix_scatter(const int32_t *__restrict__ keys_in, const int32_t *__restrict__ rows_in, const VT *__restrict__ vals_in,
+                int32_t *__restrict__ keys_out, int32_t *__restrict__ rows_out, VT *__restrict__ vals_out, int64_t n,
+                int shift, const int64_t *__restrict__ tile_off, int64_t ntiles)
+{
+    __shared__ uint32_t wc[RS_WARPS][256];
+    __shared__ int64_t toff[256];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++)
+        wc[k][tid] = 0;
+    toff[tid] = tile_off[(int64_t)tid * ntiles + blockIdx.x];
+    __syncthreads();
+
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_ITEMS;
+    int32_t key[RS_STEPS];
+    uint32_t rank[RS_STEPS];
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int k = 0; k < RS_STEPS; k++) {
+        const int64_t i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        key[k] = valid ? keys_in[i] : 0;
+        // invalid lanes get a unique pseudo-digit so they match nobody
+        const unsigned d = valid ? (unsigned)((key[k] >> shift) & 255) : 256u + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned before = __popc(peers & lt);
+        const uint32_t cur = valid ? wc[w][d] : 0u;
+        __syncwarp();
+        if (valid && before == 0)
+            wc[w][d] = cur + __popc(peers);
+        __syncwarp();
+        rank[k] = cur + before;
+    }
+    __syncthreads();
+    {
+        // exclusive prefix over the warps for digit `tid`
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < RS_WARPS; k++) {
+            uint32_t c = wc[k][tid];
+            wc[k][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_STEPS; k++) {
+        const int64_t i = wbase + k * 32 + lane;
+        if (i < n) {
+            const unsigned d = (unsigned)((key[k] >> shift) & 255);
+            const int64_t pos = toff[d] + wc[w][d] + rank[k];
+            keys_out[pos] = key[k];
+            rows_out[pos] = rows_in[i];
+            if constexpr (!std::is_same<VT, NoPayload>::value)
+                vals_out[pos] = vals_in[i];
+        }
+    }
+}
+
+// rows[i] = the row that owns nnz position i (last r with rp[r] <= i)
+template <typename RPT>
+__global__ void k_expand_rows(const RPT *__restrict__ rp, int32_t nrows, int64_t nnz, int32_t *__restrict__ rows)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz)
+        return;
+    // first r in [0, nrows] with rp[r] >= i+1, minus one
+    rows[i] = (int32_t)(lower_bound_rp(rp, 0, (int64_t)nrows + 1, i + 1) - 1);
+}
+
+template <typename CT>
+__global__ void k_col_count(const int32_t *__restrict__ ci, int64_t nnz, CT *__restrict__ cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz)
+        atomicAdd(&cnt[ci[i]], (CT)1);
+}
+
+__global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = (double)in[i];
+}
+
+template <typename RPT>
+__global__ void k_rows_unsorted(const RPT *__restrict__ rp, const int32_t *__restrict__ ci, int32_t nrows, int64_t nnz,
+                                int *__restrict__ flag)
+{
+    // entry i is out of order if it is not the first of its row and ci[i-1] > ci[i]
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i >= nnz)
+        return;
+    if (ci[i - 1] > ci[i]) {
+        // is i a row start?  (some r with rp[r] == i)
+        int64_t r = lower_bound_rp(rp, 0, (int64_t)nrows + 1, i);
+        if (!(r <= nrows && (int64_t)rp[r] == i))
+            *flag = 1;
+    }
+}
+
+struct CoreOut {
+    DevBuf rp;  // RPT[ncols+1]
+    DevBuf ci;  // int32[nnz]  (source row of every entry, i.e. the transpose's colinds)
+    DevBuf vs;  // VT[nnz]
+};
+
+static int key_bits(int32_t ncols)
+{
+    int b = 1;
+    while (b < 31 && ((int64_t)1 << b) < (int64_t)ncols)
+        b++;
+    return b;
+}
+
+// Stable counting sort of the nnz entries by column.  VT is the payload type moved
+// with each entry (NoPayload / float / double).
+template <typename RPT, typename VT>
+static int transpose_core(int32_t nrows, int32_t ncols, int64_t nnz, const RPT *rp, const int32_t *ci, const VT *vs,
+                          CoreOut &out, cudaStream_t s)
+{
+    constexpr bool HASV = !std::is_same<VT, NoPayload>::value;
+    using CT = typename std::conditional<sizeof(RPT) == 8, unsigned long long, int>::type;
+    // 1. column counts -> output rowptrs
+    DevBuf cnt;
+    CSRK_TRY(cnt.alloc_zero(sizeof(RPT) * ((size_t)ncols + 1), s));
+    CSRK_TRY(out.rp.alloc(sizeof(RPT) * ((size_t)ncols + 1), s));
+    if (nnz)
+        CSRK_LAUNCH((k_col_count<CT>), (unsigned)div_up(nnz, 256), 256, 0, s, ci, nnz, cnt.as<CT>());
+    CSRK_TRY((exclusive_scan<RPT>(ArrayLoader<RPT>{cnt.as<RPT>()}, (int64_t)ncols, out.rp.as<RPT>(), s)));
+    cnt.reset();
+    CSRK_TRY(out.ci.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    if (HASV)
+        CSRK_TRY(out.vs.alloc(sizeof(VT) * (size_t)nnz, s));
+    if (nnz == 0)
+        return CSRK_OK;
+
+    // 2. source row of every entry
+    DevBuf rows0;
+    CSRK_TRY(rows0.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    CSRK_LAUNCH((k_expand_rows<RPT>), (unsigned)div_up(nnz, 256), 256, 0, s, rp, nrows, nnz, rows0.as<int32_t>());
+
+    // 3. LSD radix passes, ping-pong; the last pass lands in out.ci / out.vs
+    const int npass = (key_bits(ncols) + 7) / 8;
+    const int64_t ntiles = div_up(nnz, RS_TILE);
+    DevBuf keysA, keysB, rowsT, valsT, hist, offs;
+    CSRK_TRY(keysA.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    if (npass > 1) {
+        CSRK_TRY(keysB.alloc(sizeof(int32_t) * (size_t)nnz, s));
+        CSRK_TRY(rowsT.alloc(sizeof(int32_t) * (size_t)nnz, s));
+        if (HASV)
+            CSRK_TRY(valsT.alloc(sizeof(VT) * (size_t)nnz, s));
+    }
+    CSRK_TRY(hist.alloc(sizeof(uint32_t) * 256 * (size_t)ntiles, s));
+    CSRK_TRY(offs.alloc(sizeof(int64_t) * (256 * (size_t)ntiles + 1), s));
+
+    const int32_t *kin = ci;
+    const int32_t *rin = rows0.as<int32_t>();
+    const VT *vin = vs;
+    for (int pass = 0; pass < npass; pass++) {
+        // choose destinations so that the final pass writes the outputs
+        const bool to_out = ((npass - 1 - pass) % 2) == 0;
+        int32_t *kout = (pass % 2 == 0) ? keysA.as<int32_t>() : keysB.as<int32_t>();
+        int32_t *rout = to_out ? out.ci.as<int32_t>() : rowsT.as<int32_t>();
+        VT *vout = HASV ? (to_out ? out.vs.as<VT>() : valsT.as<VT>()) : nullptr;
+        const int shift = 8 * pass;
+        CSRK_LAUNCH(k_radix_hist, (unsigned)ntiles, RS_BLOCK, 0, s, kin, nnz, shift, hist.as<uint32_t>(), ntiles);
+        CSRK_TRY((exclusive_scan<int64_t>(ArrayLoader<uint32_t>{hist.as<uint32_t>()}, 256 * ntiles, offs.as<int64_t>(), s)));
+        CSRK_LAUNCH((k_radix_scatter<VT>), (unsigned)ntiles, RS_BLOCK, 0, s, kin, rin, vin, kout, rout, vout, nnz, shift,
+                    offs.as<int64_t>(), ntiles);
+        kin = kout;
+        rin = rout;
+        vin = vout;
+    }
+    return CSRK_OK;
+}
+
+template <typename RPT>
+static int transpose_typed(csrk_matrix *a, int vk, CoreOut &out, cudaStream_t s)
+{
+    const RPT *rp = (const RPT *)a->rp;
+    if (vk == 4)
+        return transpose_core<RPT, float>(a->nrows, a->ncols, a->nnz, rp, a->ci, (const float *)a->vs, out, s);
+    if (vk == 8)
+        return transpose_core<RPT, double>(a->nrows, a->ncols, a->nnz, rp, a->ci, (const double *)a->vs, out, s);
+    return transpose_core<RPT, NoPayload>(a->nrows, a->ncols, a->nnz, rp, a->ci, (const NoPayload *)nullptr, out, s);
+}
+
+int transpose_run(csrk_matrix *a, int with_values, csrk_matrix **result, cudaStream_t s)
+{
+    *result = nullptr;
+    const int vk = (with_values && a->val_kind) ? a->val_kind : 0;
+    CoreOut out;
+    if (a->rp_is64)
+        CSRK_TRY(transpose_typed<int64_t>(a, vk, out, s));
+    else
+        CSRK_TRY(transpose_typed<int32_t>(a, vk, out, s));
+    csrk_matrix *m = new (std::nothrow) csrk_matrix();
+    if (!m) {
+        set_error("host allocation failed");
+        return CSRK_ENOMEM;
+    }
+    m->nrows = a->ncols;
+    m->ncols = a->nrows;
+    m->nnz = a->nnz;
+    m->rp_is64 = a->rp_is64;
+    m->val_kind = vk ? 8 : 0;  // structure.py:177: transposed values are always float64
+    if (vk == 4) {
+        DevBuf v64;
+        int rc = v64.alloc(sizeof(double) * (size_t)a->nnz, s);
+        if (rc != CSRK_OK) {
+            delete m;
+            return rc;
+        }
+        if (a->nnz) {
+            k_f32_to_f64<<<(unsigned)div_up(a->nnz, 256), 256, 0, s>>>(out.vs.as<float>(), v64.as<double>(), a->nnz);
+            g_launches.fetch_add(1);
+        }
+        m->vs = v64.release();
+    } else if (vk == 8) {
+        m->vs = out.vs.release();
+    }
+    m->rp = out.rp.release();
+    m->ci = (int32_t *)out.ci.release();
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        matrix_destroy(m, s);
+        return cuda_fail(e, "transpose", __FILE__, __LINE__);
+    }
+    *result = m;
+    return CSRK_OK;
+}
+
+template <typename RPT, typename VT>
+static int order_typed(csrk_matrix *h, cudaStream_t s)
+{
+    CoreOut t1, t2;
+    CSRK_TRY((transpose_core<RPT, VT>(h->nrows, h->ncols, h->nnz, (const RPT *)h->rp, h->ci, (const VT *)h->vs, t1, s)));
+    CSRK_TRY((transpose_core<RPT, VT>(h->ncols, h->nrows, h->nnz, t1.rp.as<RPT>(), t1.ci.as<int32_t>(), t1.vs.as<VT>(),
+                                      t2, s)));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    // rowptrs are unchanged by a within-row permutation; swap in the sorted arrays
+    dev_free(h->ci, s);
+    h->ci = (int32_t *)t2.ci.release();
+    if (!std::is_same<VT, NoPayload>::value) {
+        dev_free(h->vs, s);
+        h->vs = t2.vs.release();
+    }
+    return CSRK_OK;
+}
+
+int order_columns_run(csrk_matrix *h, cudaStream_t s)
+{
+    if (h->nnz < 2)
+        return CSRK_OK;
+    // cheap exit: already sorted (the reference's bubble sort is O(n) then, too)
+    DevBuf flag;
+    CSRK_TRY(flag.alloc_zero(sizeof(int), s));
+    if (h->rp_is64)
+        CSRK_LAUNCH((k_rows_unsorted<int64_t>), (unsigned)div_up(h->nnz - 1, 256), 256, 0, s, (const int64_t *)h->rp,
+                    h->ci, h->nrows, h->nnz, flag.as<int>());
+    else
+        CSRK_LAUNCH((k_rows_unsorted<int32_t>), (unsigned)div_up(h->nnz - 1, 256), 256, 0, s, (const int32_t *)h->rp,
+                    h->ci, h->nrows, h->nnz, flag.as<int>());
+    int unsorted = 0;
+    CSRK_CUDA(cudaMemcpyAsync(&unsorted, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    if (!unsorted)
+        return CSRK_OK;
+    if (h->rp_is64) {
+        if (h->val_kind == 4) return order_typed<int64_t, float>(h, s);
+        if (h->val_kind == 8) return order_typed<int64_t, double>(h, s);
+        return order_typed<int64_t, NoPayload>(h, s);
+    }
+    if (h->val_kind == 4) return order_typed<int32_t, float>(h, s);
+    if (h->val_kind == 8) return order_typed<int32_t, double>(h, s);
+    return order_typed<int32_t, NoPayload>(h, s);
+}
+
+}  // namespace csrk

@@ -1,0 +1,125 @@
+/*
+ * csrk.h -- C ABI of libcsr_cuda.so, the B200 (sm_100a) kernel backend for
+ * lenskit/csr's kernel contract.
+ *
+ * The reference has no C ABI for this path: its boundary is the Python module
+ * protocol `csr.kernels.<name>` (docs/kernels.rst:61-104, csr/kernel.py:9-16).
+ * Its one native precedent is the MKL shim (csr/kernels/mkl/mkl_ops.h:11-31);
+ * the entry points below are what a `csr.kernels.cuda` module binds through
+ * ctypes, and each cites the reference function it stands in for.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  `csrk_h` is an opaque handle owning device
+ *     memory; host callers never see device pointers except through the *_dev
+ *     entry points (used by the multi-GPU layer and the benchmark, which own
+ *     device buffers of their own).
+ *   - Every function returns an int status: 0 = ok, else a CSRK_E* code;
+ *     csrk_last_error() gives the message for the calling thread.  Nothing
+ *     aborts the process (unlike mkl_ops.c:18-45).
+ *   - rowptrs are int32 or int64 (`rp_is64`), colinds int32, values float32,
+ *     float64 or absent (`val_kind` = 4, 8, 0) -- the dtype rules of
+ *     csr/csr.py:79-100.
+ *   - Host-pointer entry points synchronise before returning.  *_dev entry
+ *     points enqueue on the given stream (0 = the library's own stream) and
+ *     return without synchronising.
+ *   - Re-entrant: concurrent calls from several threads on distinct or shared
+ *     read-only handles are legal (the numba kernels are nogil:
+ *     numba/__init__.py:55, multiply.py:13,41).  csrk_order_columns,
+ *     csrk_filter_zeros and csrk_free mutate their handle.
+ */
+#ifndef CSRK_H
+#define CSRK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct csrk_matrix *csrk_h;
+
+enum {
+    CSRK_OK = 0,
+    CSRK_EARG = 1,      /* bad argument / shape mismatch -> ValueError            */
+    CSRK_ENOMEM = 2,    /* device or host allocation failed -> MemoryError        */
+    CSRK_ECUDA = 3,     /* CUDA runtime error -> RuntimeError                     */
+    CSRK_ENODEV = 4,    /* no usable CUDA device -> RuntimeError                  */
+    CSRK_EOVERFLOW = 5  /* a size exceeds what the output dtype can address       */
+};
+
+/* ---- library / device context ------------------------------------------- */
+int csrk_version(void);
+const char *csrk_last_error(void);
+/* Select the device for the calling process (one process per GPU) and create
+ * the library stream + memory pool.  Idempotent for the same device. */
+int csrk_init(int device);
+int csrk_shutdown(void);
+/* sm count, HBM bytes (total, free) of the active device */
+int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *cc_major, int *cc_minor);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t csrk_launch_count(void);
+int csrk_synchronize(void);
+
+/* ---- handle lifecycle: to_handle / from_handle / release_handle ----------
+ * numba/__init__.py:16-44 (identity there); precedent lk_mkl_spcreate /
+ * lk_mkl_spexport_p / lk_mkl_spfree, mkl_ops.h:11-21. */
+/* H2D copy of the three arrays; the matrix stays resident until csrk_free. */
+int csrk_create(int32_t nrows, int32_t ncols, int64_t nnz,
+                const void *rowptrs, int rp_is64,
+                const int32_t *colinds,
+                const void *values, int val_kind,
+                csrk_h *out);
+/* Same, from device pointers (D2D copy on `stream`). */
+int csrk_create_dev(int32_t nrows, int32_t ncols, int64_t nnz,
+                    const void *d_rowptrs, int rp_is64,
+                    const int32_t *d_colinds,
+                    const void *d_values, int val_kind,
+                    void *stream, csrk_h *out);
+int csrk_free(csrk_h h);
+int csrk_dims(csrk_h h, int32_t *nrows, int32_t *ncols, int64_t *nnz, int *rp_is64, int *val_kind);
+/* D2H copy-out into caller-owned buffers sized from csrk_dims (values may be
+ * NULL when val_kind == 0). */
+int csrk_export(csrk_h h, void *rowptrs, int32_t *colinds, void *values);
+/* Borrow the device arrays (valid until csrk_free / a mutating call). */
+int csrk_device_ptrs(csrk_h h, void **d_rowptrs, int32_t **d_colinds, void **d_values);
+/* Rows [begin, end) as a new handle with rebased rowptrs: the device form of
+ * subset_rows, csr/structure.py:70-81 (used for sharding, csr.py:599-621). */
+int csrk_subset_rows(csrk_h h, int32_t begin, int32_t end, csrk_h *out);
+
+/* ---- mult_vec: numba/__init__.py:55-67; lk_mkl_spmv, mkl_ops.h:29 --------
+ * y[r] = sum_i x[colinds[i]] * (values[i] or 1), float64 accumulate, float64 y.
+ * x_kind = 4 (float32) or 8 (float64).  Host pointers (pinned or pageable). */
+int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y);
+/* Device pointers; y has nrows doubles. */
+int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stream);
+
+/* ---- mult_ab / mult_abt: multiply.py:13-57; lk_mkl_spmab/spmabt ----------
+ * C = A*B (a.ncols == b.nrows) and C = A*B^T (a.ncols == b.ncols) as a NEW
+ * handle the caller frees.  Output: float64 values, int32 colinds sorted
+ * ascending within each row, rowptrs int32 (int64 when out-nnz > INT32_MAX,
+ * the rule of csr.py:90-93). */
+int csrk_spgemm(csrk_h a, csrk_h b, csrk_h *c);
+int csrk_spgemm_abt(csrk_h a, csrk_h b, csrk_h *c);
+/* Work counters of the last product that produced `c`: products P (sum over
+ * A's entries of the referenced B row length) and out-nnz Z. */
+int csrk_spgemm_stats(csrk_h c, int64_t *products, int64_t *out_nnz);
+
+/* ---- transpose: csr/structure.py:172-247 ---------------------------------
+ * Stable CSR->CSC.  rowptr dtype follows the input; values become float64
+ * (structure.py:177); with_values == 0 (or a value-less input) gives a
+ * structure-only result. */
+int csrk_transpose(csrk_h a, int with_values, csrk_h *at);
+
+/* ---- order_columns: numba/__init__.py:47-52 -> structure.py:156-169 ------
+ * In-place ascending column sort inside each row, values carried along; equal
+ * columns keep their relative order (the bubble sort is stable). */
+int csrk_order_columns(csrk_h h);
+
+/* ---- _filter_zeros: csr/_struct.py:61-79 ----------------------------------
+ * In-place removal of stored zeros (no-op for value-less matrices). */
+int csrk_filter_zeros(csrk_h h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSRK_H */
