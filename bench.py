@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""
+bench.py -- the hot path of BASELINE.json measured on B200.
+
+Headline (one JSON line on stdout, rank 0):
+    metric  "spmv_hbm_gbs"  algorithmic HBM GB/s of mult_vec (SURVEY.md 8d:
+            nnz*(4+V) + (nrows+1)*R + ncols*X + nrows*8 bytes per call), whole job
+    config  BASELINE.json configs[1]: synthetic power-law CSR, 1M x 1M, 100M nnz,
+            float32 values, float32 x, float64 y, one such row block PER GPU (weak
+            scaling: N GPUs hold an (N*1M) x (N*1M) matrix of N*100M nnz; a step is
+            broadcast(x) -> local SpMV -> all-gather(y) over NCCL)
+    value   matrix, x and y resident in HBM, CUDA-event time on the launching
+            stream, max over ranks
+    e2e     the same metric through the kernel module's public call
+            ``K.mult_vec(h, x)`` with HOST (pinned) x and y: H2D of x and D2H of y
+            inside the timed region, the matrix resident (that is what a handle is)
+    roofline / cpu_baseline / clocks / gpu_launches as the task contract asks.
+    spgemm  A*A^T (mult_abt) out-nnz/s on BASELINE.json configs[2] (item-item,
+            100k users x 50k items, 20M nnz, f64), N=1 only, with its own
+            roofline and CPU numbers.
+
+``--impl reference`` times the reference's CPU implementation of the path (the
+oracle port of the numba kernel; the reference itself is Python/numba and does not
+exist on the GPU box) on all host threads, same metric and config, each step a
+bounded row-block sample.
+"""
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PER_GPU_ROWS = 1_000_000
+PER_GPU_NNZ = 100_000_000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def spmv_bytes(nnz, nrows, ncols, val_bytes, x_bytes, rp_bytes=4):
+    return nnz * (4 + val_bytes) + (nrows + 1) * rp_bytes + ncols * x_bytes + nrows * 8
+
+
+def csr_bytes(m):
+    v = 0 if m.values is None else m.values.dtype.itemsize
+    return m.nnz * (4 + v) + (m.nrows + 1) * m.rowptrs.dtype.itemsize
+
+
+class ClockSampler:
+    "SM clock + throttle reasons during the timed region (NVML; nvidia-smi as a fallback)."
+
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self._nv = None
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self._nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_block(rank, world, scale, col_skew):
+    "This rank's row block of the weak-scaled cfg2 matrix (global column count)."
+    from csr_b200 import synth
+    nr = max(int(PER_GPU_ROWS * scale), 64)
+    nnz = 100 * nr
+    return synth.powerlaw_csr(nr, nr * world, nnz, seed=2 + 1000 * rank, dtype="f4", alpha=1.0, col_skew=col_skew)
+
+
+def cpu_count():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_best(fn, reps):
+    best = float("inf")
+    for _ in range(reps):
+        t = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t)
+    return best
+
+
+# --------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from csr_b200 import _native
+    from csr_b200.kernels import get_kernel
+    from csr_b200.dist import DistSpMV
+    K = get_kernel("cuda")
+    W = args.warmup
+    steps = args.steps
+    peak, peak_src = measured_peak()
+
+    t0 = time.perf_counter()
+    A = make_block(rank, world, args.scale, args.col_skew)
+    t_gen = time.perf_counter() - t0
+    x_host = np.random.default_rng(77).standard_normal(A.ncols).astype(np.float32)
+    row_counts = [A.nrows] * world
+    t0 = time.perf_counter()
+    ds = DistSpMV(A, row_counts, x_dtype="f4", kernel=K)
+    t_handle = time.perf_counter() - t0
+    ds.set_x(x_host)
+    log(f"[rank {rank}] block {A}  gen {t_gen:.1f}s  to_handle {t_handle:.2f}s")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    local_bytes = ds.bytes_per_step(A.nnz, 4)
+    total_bytes = allsum(float(local_bytes))
+
+    # ---- value: device-resident, whole step (broadcast + SpMV + all-gather)
+    for _ in range(W):
+        ds.step()
+    barrier()
+    n0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(steps):
+            ds.step()
+        e1.record()
+        torch.cuda.synchronize()
+    barrier()
+    launches = _native.launch_count() - n0
+    ms_step = allmax(e0.elapsed_time(e1) / steps)
+    value = total_bytes / (ms_step * 1e-3) / 1e9
+
+    # ---- the dominant kernel alone (local SpMV, no collectives) for the roofline
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seg = ds.ybuf[ds.rank * ds.pad: ds.rank * ds.pad + A.nrows]
+    for _ in range(3):
+        ds.compute(ds.x, seg)
+    torch.cuda.synchronize()
+    e2.record()
+    for _ in range(steps):
+        ds.compute(ds.x, seg)
+    e3.record()
+    torch.cuda.synchronize()
+    ms_kernel = e2.elapsed_time(e3) / steps
+    achieved = local_bytes / (ms_kernel * 1e-3) / 1e9
+
+    # ---- e2e: public kernel call, host (pinned) x and y
+    xp = torch.empty(A.ncols, dtype=torch.float32).pin_memory()
+    xp.copy_(torch.from_numpy(x_host))
+    yp = torch.empty(A.nrows, dtype=torch.float64).pin_memory()
+    xn, yn = xp.numpy(), yp.numpy()
+    for _ in range(W):
+        K.mult_vec(ds.handle, xn, out=yn)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        K.mult_vec(ds.handle, xn, out=yn)
+    e2e_s = allmax((time.perf_counter() - t0) / steps)
+    barrier()
+    e2e_val = total_bytes / e2e_s / 1e9
+
+    # sanity: the timed path computes the right thing (size-independent check on a sample of rows)
+    y_dev = ds.ybuf[ds.rank * ds.pad: ds.rank * ds.pad + A.nrows].cpu().numpy()
+    assert np.allclose(y_dev, yn, rtol=1e-9, atol=1e-9), "device-resident and host-API results differ"
+
+    out = {
+        "metric": "spmv_hbm_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": steps,
+        "warmup": W, "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 values/x, f64 accumulate", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[1]: synthetic power-law CSR, %dx%d, %d nnz per GPU, float32, mult_vec"
+                        % (A.nrows, A.nrows, A.nnz),
+            "global_shape": [A.nrows * world, A.ncols], "global_nnz": A.nnz * world,
+            "row_lengths": "rank-size power law alpha=1.0, mean 100, cap ncols, random row order",
+            "columns": "stratified uniform" if args.col_skew == 1.0 else f"stratified, skew t^{args.col_skew}",
+            "parallelism": f"row-partitioned x{world}; step = NCCL broadcast(x) + local SpMV + all-gather(y)",
+            "l2_policy": "inputs (>=0.8 GB per GPU) larger than the 126 MB L2; no flush needed",
+            "bytes_per_step": int(total_bytes), "scale": args.scale,
+        },
+        "e2e": {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": int(A.ncols * 4 * world),
+                "d2h_bytes_per_step": int(A.nrows * 8 * world), "ms_per_step": round(e2e_s * 1e3, 5),
+                "call": "csr_b200.kernels.cuda.mult_vec(handle, x_pinned, out=y_pinned); matrix resident",
+                "to_handle_s": round(t_handle, 3)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": args.traffic, "peak_source": peak_src,
+                     "kernel": "k_spmv_tile<int,float,float> (+k_spmv_fixup)", "kernel_ms": round(ms_kernel, 5),
+                     "frac_of_nominal_8000": round(achieved / 8000.0, 4)},
+        "clocks": clk.summary(),
+    }
+
+    if world == 1 and rank == 0:
+        out["cpu_baseline"] = cpu_baseline_spmv(A, x_host, yn)
+        if args.spgemm_scale > 0:
+            ds.close()
+            del ds
+            out["spgemm"] = bench_spgemm(args, K, peak)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_spmv(A, x, y_gpu):
+    "The oracle port of the numba mult_vec on this box's host cores: serial (as shipped) and all cores."
+    from oracle import oracle as orc
+    cores = cpu_count()
+    M = orc.as_mat(A)
+    # bounded sample: the leading row block holding ~20% of the nnz
+    cut = int(np.searchsorted(M.rowptrs, M.nnz // 5))
+    S = orc.subset_rows(M, 0, max(cut, 1))
+    b = spmv_bytes(S.nnz, S.nrows, S.ncols, 4, 4)
+    y_ref = orc.mult_vec(S, x)
+    # parity at full size: the timed GPU path against the oracle on the sampled rows (f32 inputs: rtol 1e-5)
+    scale = float(np.abs(y_ref).max())
+    err = float(np.abs(y_gpu[:S.nrows] - y_ref).max())
+    assert np.allclose(y_gpu[:S.nrows], y_ref, rtol=1e-5, atol=1e-5 * scale), f"SpMV parity failed: max err {err}"
+    t1 = time_best(lambda: orc.mult_vec(S, x), 3)
+    orc.mult_vec_threads(S, x, cores)
+    tn = time_best(lambda: orc.mult_vec_threads(S, x, cores), 5)
+    return {"value": round(b / tn / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"leading row block with {S.nnz} of {M.nnz} nnz ({S.nrows} rows), best of 5",
+            "parity": f"GPU y == oracle y on {S.nrows} rows (rtol 1e-5), max abs err {err:.3e}",
+            "serial_value": round(b / t1 / 1e9, 3), "serial_note": "1 core: the numba kernel as shipped is serial",
+            "cpu": cpu_model()}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def bench_spgemm(args, K, peak):
+    "A*A^T (item-item, cfg3) on one GPU: out-nnz/s, products/s, fraction of the HBM roofline."
+    import torch
+    from csr_b200 import synth
+    from oracle import oracle as orc
+    R = synth.cfg3_ratings(args.spgemm_scale)
+    rh = K.to_handle(R)
+    mh = K.transpose(rh)               # M = ratings^T  (items x users)
+    K.release_handle(rh)
+    M = K.from_handle(mh)
+
+    def once():
+        ch = K.mult_abt(mh, mh)
+        st = K.spgemm_stats(ch)
+        K.release_handle(ch)
+        return st
+
+    once()
+    reps = 3
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        st = once()
+    dt = (time.perf_counter() - t0) / reps
+    Z, P = st["out_nnz"], st["products"]
+    b_algo = 2 * csr_bytes(M) + Z * 12 + (M.nrows + 1) * 4      # bytes(A)+bytes(B)+bytes(C)
+    b_tr = csr_bytes(M) + M.nnz * 12 + (M.ncols + 1) * 4        # the transpose inside mult_abt
+    # CPU: the oracle on a leading row block sized for a few seconds, all cores
+    cores = cpu_count()
+    Mo = orc.as_mat(M)
+    Mt = orc.transpose(Mo)
+    rows = max(int(Mo.nrows * min(1.0, 4e8 / max(P, 1))), 1)
+    S = orc.subset_rows(Mo, 0, rows)
+    t0 = time.perf_counter()
+    parts = orc.mult_threads(S, Mt, cores)
+    tcpu = time.perf_counter() - t0
+    zs = sum(p.nnz for p in parts)
+    K.release_handle(mh)
+    return {"metric": "spgemm_abt_out_nnz_per_s", "value": round(Z / dt, 1), "unit": "nnz/s",
+            "workload": f"BASELINE configs[2] x{args.spgemm_scale}: M={M.nrows}x{M.ncols}, {M.nnz} nnz f64, mult_abt(M,M)",
+            "out_nnz": Z, "products": P, "compression": round(P / max(Z, 1), 2), "ms": round(dt * 1e3, 3),
+            "products_per_s": round(P / dt, 1),
+            "roofline": {"bound": "hbm", "achieved": round((b_algo + b_tr) / dt / 1e9, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round((b_algo + b_tr) / dt / 1e9 / peak, 4),
+                         "bytes": "bytes(A)+bytes(B)+bytes(C)+transpose", "traffic": None},
+            "cpu_baseline": {"value": round(zs / tcpu, 1), "unit": "nnz/s", "cores": cores, "kind": "port",
+                             "sample": f"first {rows} of {Mo.nrows} rows of A ({zs} out-nnz), one run, transpose excluded"}}
+
+
+# ---------------------------------------------------------------- reference
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    cores = cpu_count()
+    A = make_block(0, world, args.scale, args.col_skew)
+    x = np.random.default_rng(77).standard_normal(A.ncols).astype(np.float32)
+    M = orc.as_mat(A)
+    cut = int(np.searchsorted(M.rowptrs, M.nnz // 5))
+    S = orc.subset_rows(M, 0, max(cut, 1))
+    b = spmv_bytes(S.nnz, S.nrows, S.ncols, 4, 4)
+    for _ in range(args.warmup):
+        orc.mult_vec_threads(S, x, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.mult_vec_threads(S, x, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = round(b / dt / 1e9, 3)
+    sample = f"leading row block with {S.nnz} of {M.nnz} nnz per step, {cores} threads over row blocks"
+    print(json.dumps({
+        "impl": "reference", "metric": "spmv_hbm_gbs", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 values/x, f64 accumulate", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: synthetic power-law CSR, %dx%d, %d nnz, float32, mult_vec"
+                               % (A.nrows, A.nrows, A.nnz), "scale": args.scale},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
+                         "cpu": cpu_model()},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only)")
+    ap.add_argument("--col-skew", type=float, default=1.0)
+    ap.add_argument("--spgemm-scale", type=float, default=0.0, help="scale of configs[2] for the A*A^T leg (0 = skip)")
+    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the SpMV kernel, if known")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -239,6 +240,14 @@ int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *
 
 int64_t csrk_launch_count(void) { return g_launches.load(); }
 
+int csrk_get_stream(void **stream)
+{
+    CSRK_ARG(stream != nullptr, "stream pointer is NULL");
+    CSRK_TRY(ensure_init());
+    *stream = (void *)ctx().stream;
+    return CSRK_OK;
+}
+
 int csrk_synchronize(void)
 {
     CSRK_TRY(ensure_init());
@@ -285,7 +294,7 @@ int csrk_create_dev(int32_t nrows, int32_t ncols, int64_t nnz, const void *d_row
                     const int32_t *d_colinds, const void *d_values, int val_kind, void *stream, csrk_h *out)
 {
     CSRK_TRY(ensure_init());
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx().stream;
+    cudaStream_t s = (cudaStream_t)stream;
     return create_impl(nrows, ncols, nnz, d_rowptrs, rp_is64, d_colinds, d_values, val_kind, s,
                        cudaMemcpyDeviceToDevice, out);
 }
@@ -356,8 +365,11 @@ int csrk_subset_rows(csrk_h h, int32_t begin, int32_t end, csrk_h *out)
         st = tmp[0];
         ed = tmp[1];
     } else {
-        st = *(int32_t *)&tmp[0];
-        ed = *(int32_t *)&tmp[1];
+        int32_t a32, b32;
+        memcpy(&a32, &tmp[0], 4);
+        memcpy(&b32, &tmp[1], 4);
+        st = a32;
+        ed = b32;
     }
     const int64_t nnz = ed - st;
     const int32_t nr = end - begin;
@@ -394,7 +406,7 @@ int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stre
     CSRK_ARG(h->ncols == 0 || d_x != nullptr, "x is NULL");
     CSRK_ARG(h->nrows == 0 || d_y != nullptr, "y is NULL");
     CSRK_TRY(ensure_init());
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx().stream;
+    cudaStream_t s = (cudaStream_t)stream;
     return spmv_run(h, d_x, x_kind, d_y, s);
 }
 

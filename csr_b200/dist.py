@@ -1,0 +1,214 @@
+"""
+Row-partitioned multi-GPU SpMV and SpGEMM: one process per GPU, torch.distributed
+(NCCL over NVLink 5 / NVSwitch) for the exchange steps, the cuda kernel for the
+local work.
+
+The partition is the parallel form of the reference's sequential sharding
+(``CSR._shard_rows`` / ``_assemble_shards``, csr/csr.py:599-650): contiguous row
+blocks of about equal nnz, ``split_k = searchsorted(rowptrs, k*nnz/N)``.
+
+* SpMV: every rank holds its row block and a full copy of x.  A step is
+  ``broadcast(x)`` from the root, the local SpMV on the same stream, and an
+  all-gather of the y segments (padded to the longest block; there is no
+  all-gather-v).
+* SpGEMM (A*B, A*B^T): B is replicated by three broadcasts (rowptrs, colinds,
+  values); each rank multiplies its A block; output row blocks stay distributed,
+  and ``assemble`` concatenates them on every rank with the int64 rowptr
+  fix-up of ``_assemble_shards`` (csr.py:632-638).
+
+The local compute is injected (``compute=``) so the host-side logic can be tested
+with world_size 2 on the gloo backend; the default is the cuda kernel and there
+is no other product path.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def partition_rows(rowptrs, nparts: int):
+    """Row boundaries ``[b_0=0, ..., b_N=nrows]`` giving blocks of ~equal nnz
+    (the rule of csr.py:609-614 applied at k*nnz/N)."""
+    rp = np.asarray(rowptrs)
+    nrows = len(rp) - 1
+    nnz = int(rp[-1])
+    cuts = [0]
+    for k in range(1, nparts):
+        s = int(np.searchsorted(rp, (nnz * k) // nparts, side="left"))
+        cuts.append(min(max(s, cuts[-1]), nrows))
+    cuts.append(nrows)
+    return cuts
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+class DistSpMV:
+    """y = A x with A row-partitioned over the ranks of ``group``.
+
+    ``local`` is this rank's row block (a CSR with the GLOBAL column count).
+    ``row_counts[r]`` is the number of rows rank r owns.
+    """
+
+    def __init__(self, local, row_counts, *, x_dtype="f4", device=None, group=None, compute=None, kernel=None):
+        import torch
+        self.torch = torch
+        self.group = group
+        dist = _dist()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.row_counts = [int(c) for c in row_counts]
+        assert len(self.row_counts) == self.world
+        assert local.nrows == self.row_counts[self.rank]
+        self.nrows = sum(self.row_counts)
+        self.ncols = int(local.ncols)
+        self.pad = max(self.row_counts) if self.row_counts else 0
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        tdt = torch.float32 if np.dtype(x_dtype) == np.float32 else torch.float64
+        self.x = torch.zeros(self.ncols, dtype=tdt, device=self.device)
+        # gather buffer: world segments of `pad` doubles; this rank's SpMV writes straight into its segment
+        self.ybuf = torch.zeros(self.world * self.pad, dtype=torch.float64, device=self.device)
+        self.handle = None
+        if compute is None:
+            if kernel is None:
+                from .kernels import get_kernel
+                kernel = get_kernel("cuda")
+            self.kernel = kernel
+            self.handle = kernel.to_handle(local)
+            compute = self._cuda_compute
+        self.compute = compute
+
+    def _cuda_compute(self, x, y):
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self.kernel.mult_vec_dev(self.handle, x.data_ptr(), x.element_size(), y.data_ptr(), stream)
+
+    def set_x(self, x_host):
+        "Load x on the root (other ranks receive it in step())."
+        self.x.copy_(self.torch.as_tensor(np.ascontiguousarray(x_host)).to(self.x.dtype), non_blocking=False)
+
+    def step(self, broadcast_x: bool = True):
+        """One distributed SpMV; returns the full y (device tensor view, nrows doubles
+        once ``result()`` strips the padding)."""
+        dist = _dist()
+        if self.world > 1 and broadcast_x:
+            dist.broadcast(self.x, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+        seg = self.ybuf[self.rank * self.pad: self.rank * self.pad + self.row_counts[self.rank]]
+        self.compute(self.x, seg)
+        if self.world > 1:
+            mine = self.ybuf[self.rank * self.pad:(self.rank + 1) * self.pad]
+            dist.all_gather_into_tensor(self.ybuf, mine, group=self.group)
+        return self.ybuf
+
+    def result(self) -> np.ndarray:
+        "The assembled y on the host (padding removed)."
+        y = self.ybuf.cpu().numpy()
+        return np.concatenate([y[r * self.pad: r * self.pad + c] for r, c in enumerate(self.row_counts)])
+
+    def bytes_per_step(self, nnz_local: int, val_bytes: int, rp_bytes: int = 4) -> int:
+        "Algorithmic HBM bytes of THIS rank's SpMV (SURVEY 8d): nnz*(4+V) + (rows+1)*R + ncols*X + rows*8."
+        nr = self.row_counts[self.rank]
+        return nnz_local * (4 + val_bytes) + (nr + 1) * rp_bytes + self.ncols * self.x.element_size() + nr * 8
+
+    def close(self):
+        if self.handle is not None:
+            self.kernel.release_handle(self.handle)
+            self.handle = None
+
+
+def replicate_csr(mat, *, src: int = 0, group=None, device=None, csr_cls=None):
+    """Broadcast a CSR from ``src`` to every rank (three NCCL broadcasts + one of the
+    shape); returns the host CSR on ``src`` and a rebuilt host CSR elsewhere.
+    Used to replicate B (or A^T) for the distributed SpGEMM."""
+    import torch
+    dist = _dist()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mat
+    rank = dist.get_rank(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if torch.cuda.is_available() else torch.device("cpu"))
+    meta = torch.zeros(6, dtype=torch.int64, device=dev)
+    if rank == src:
+        vk = 0 if mat.values is None else mat.values.dtype.itemsize
+        meta = torch.tensor([mat.nrows, mat.ncols, mat.nnz, mat.rowptrs.dtype.itemsize, vk, 0], dtype=torch.int64, device=dev)
+    dist.broadcast(meta, src=src, group=group)
+    nrows, ncols, nnz, rpw, vk, _ = (int(v) for v in meta.cpu())
+    rdt = torch.int64 if rpw == 8 else torch.int32
+    vdt = {0: None, 4: torch.float32, 8: torch.float64}[vk]
+
+    def bc(host, n, dt):
+        t = torch.as_tensor(np.ascontiguousarray(host)).to(dev) if rank == src else torch.empty(n, dtype=dt, device=dev)
+        dist.broadcast(t, src=src, group=group)
+        return t
+
+    rp = bc(mat.rowptrs if rank == src else None, nrows + 1, rdt)
+    ci = bc(mat.colinds if rank == src else None, nnz, torch.int32)
+    vs = bc(mat.values if rank == src else None, nnz, vdt) if vk else None
+    if rank == src:
+        return mat
+    if csr_cls is None:
+        from .csr import CSR as csr_cls
+    return csr_cls(nrows, ncols, nnz, rp.cpu().numpy(), ci.cpu().numpy(), None if vs is None else vs.cpu().numpy(),
+                   _cast=False)
+
+
+def dist_multiply(a_local, b, *, transpose: bool = False, kernel=None, multiply=None):
+    """This rank's block of C = A B (or A B^T): ``a_local`` is the rank's row block
+    of A, ``b`` the replicated operand.  Returns the local block as a host CSR at
+    kernel level (stored zeros kept).  ``multiply`` injects the local product for
+    CPU tests; the default is the cuda kernel."""
+    if multiply is not None:
+        return multiply(a_local, b, transpose)
+    if kernel is None:
+        from .kernels import get_kernel
+        kernel = get_kernel("cuda")
+    ah, bh = kernel.to_handle(a_local), kernel.to_handle(b)
+    try:
+        ch = kernel.mult_abt(ah, bh) if transpose else kernel.mult_ab(ah, bh)
+        try:
+            return kernel.from_handle(ch)
+        finally:
+            kernel.release_handle(ch)
+    finally:
+        kernel.release_handle(ah)
+        kernel.release_handle(bh)
+
+
+def assemble_blocks(local, *, group=None, device=None, csr_cls=None):
+    """Concatenate the ranks' output row blocks on every rank: all-gather of the
+    block sizes, rowptr offset fix-up in int64 (``_assemble_shards``,
+    csr.py:632-638), padded all-gather of colinds / values."""
+    import torch
+    dist = _dist()
+    if csr_cls is None:
+        from .csr import CSR as csr_cls
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if torch.cuda.is_available() else torch.device("cpu"))
+    has_v = local.values is not None
+    sizes = torch.tensor([local.nrows, local.nnz, local.ncols], dtype=torch.int64, device=dev)
+    allsz = torch.zeros(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allsz, sizes, group=group)
+    allsz = allsz.cpu().numpy().reshape(world, 3)
+    max_rows, max_nnz = int(allsz[:, 0].max()), int(allsz[:, 1].max())
+
+    def gather(host, n, pad, dt):
+        t = torch.zeros(pad, dtype=dt, device=dev)
+        if n:
+            t[:n] = torch.as_tensor(np.ascontiguousarray(host)).to(dev).to(dt)
+        out = torch.zeros(world * pad, dtype=dt, device=dev)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.cpu().numpy().reshape(world, pad)
+
+    rps = gather(np.asarray(local.rowptrs, np.int64), local.nrows + 1, max_rows + 1, torch.int64)
+    cis = gather(local.colinds, local.nnz, max(max_nnz, 1), torch.int32)
+    vss = gather(local.values, local.nnz, max(max_nnz, 1), torch.float64) if has_v else None
+    blocks = []
+    for r in range(world):
+        nr, nz, nc = (int(v) for v in allsz[r])
+        blocks.append(csr_cls(nr, nc, nz, rps[r, :nr + 1], cis[r, :nz], None if vss is None else vss[r, :nz]))
+    return csr_cls._assemble_shards(blocks)

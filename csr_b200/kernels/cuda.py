@@ -129,7 +129,11 @@ def from_handle(h: cuda_h):
     vs = None if vk.value == 0 else np.empty(nnz.value, np.float32 if vk.value == 4 else np.float64)
     N.check(L.csrk_export(raw, _ptr(rps), _ptr(cis), _ptr(vs)), "from_handle")
     cls = h.csr_cls or _default_csr_cls()
-    return cls(nr.value, nc.value, nnz.value, rps, cis, vs)
+    try:
+        # keep the handle's dtypes exactly (int64 rowptrs stay int64, as the numba kernel's do)
+        return cls(nr.value, nc.value, nnz.value, rps, cis, vs, _cast=False)
+    except TypeError:
+        return cls(nr.value, nc.value, nnz.value, rps, cis, vs)
 
 
 def release_handle(h: cuda_h) -> None:
@@ -215,7 +219,8 @@ def spgemm_stats(h: cuda_h) -> dict:
 
 
 def mult_vec_dev(h: cuda_h, x_ptr: int, x_itemsize: int, y_ptr: int, stream: int = 0) -> None:
-    """Device-pointer SpMV, enqueued on ``stream`` (0 = the library stream), no
+    """Device-pointer SpMV, enqueued on the cudaStream_t ``stream`` (used verbatim: 0 is
+    CUDA's default stream, e.g. ``torch.cuda.current_stream().cuda_stream``), no
     synchronisation: for callers that own device buffers (multi-GPU layer, bench)."""
     N.check(N.lib().csrk_spmv_dev(_live(h), C.c_void_p(x_ptr), int(x_itemsize), C.c_void_p(y_ptr),
                                   C.c_void_p(stream)), "mult_vec_dev")
@@ -230,6 +235,13 @@ def from_device_arrays(nrows, ncols, nnz, rowptrs_ptr, rp_is64, colinds_ptr, val
                                  int(val_kind), C.c_void_p(stream), C.byref(out))
     N.check(rc, "from_device_arrays")
     return cuda_h(out.value, nrows, ncols, nnz, csr_cls)
+
+
+def library_stream() -> int:
+    "The library's own stream as an integer cudaStream_t."
+    out = C.c_void_p()
+    N.check(N.lib().csrk_get_stream(C.byref(out)), "get_stream")
+    return out.value or 0
 
 
 def synchronize() -> None:

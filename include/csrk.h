@@ -19,9 +19,11 @@
  *   - rowptrs are int32 or int64 (`rp_is64`), colinds int32, values float32,
  *     float64 or absent (`val_kind` = 4, 8, 0) -- the dtype rules of
  *     csr/csr.py:79-100.
- *   - Host-pointer entry points synchronise before returning.  *_dev entry
- *     points enqueue on the given stream (0 = the library's own stream) and
- *     return without synchronising.
+ *   - Host-pointer entry points run on the library's own stream and synchronise
+ *     before returning.  *_dev entry points enqueue on the cudaStream_t passed as
+ *     `stream` -- used verbatim, so NULL is CUDA's default stream, as in every
+ *     CUDA API; csrk_get_stream() returns the library stream -- and return
+ *     without synchronising.
  *   - Re-entrant: concurrent calls from several threads on distinct or shared
  *     read-only handles are legal (the numba kernels are nogil:
  *     numba/__init__.py:55, multiply.py:13,41).  csrk_order_columns,
@@ -59,6 +61,8 @@ int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t csrk_launch_count(void);
 int csrk_synchronize(void);
+/* the library's own (non-blocking) stream, as a cudaStream_t */
+int csrk_get_stream(void **stream);
 
 /* ---- handle lifecycle: to_handle / from_handle / release_handle ----------
  * numba/__init__.py:16-44 (identity there); precedent lk_mkl_spcreate /

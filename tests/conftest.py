@@ -9,13 +9,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from hypothesis import HealthCheck, settings  # noqa: E402
+from hypothesis import HealthCheck, Phase, settings  # noqa: E402
 
 logging.getLogger('numba').setLevel(logging.INFO)
 
 # hypothesis profiles, as the reference's conftest.py:41-47
+# no shrink phase: a failing draw is reported as drawn (shrinking through a GPU call took minutes)
 settings.register_profile('default', deadline=None, max_examples=60,
-                          suppress_health_check=list(HealthCheck))
+                          suppress_health_check=list(HealthCheck),
+                          phases=[Phase.explicit, Phase.reuse, Phase.generate, Phase.target])
 settings.register_profile('large', settings.get_profile('default'), max_examples=2000)
 settings.register_profile('fast', settings.get_profile('default'), max_examples=20)
 settings.load_profile(os.environ.get('HYPOTHESIS_PROFILE', 'default'))

@@ -1,0 +1,230 @@
+"""
+GPU: larger seeded inputs (many SpMV tiles, every SpGEMM bin, multi-pass radix
+transposes) against the oracle, plus size-independent properties: row-block
+independence (virtual ranks), (A^T)^T == A, linearity of mult_vec, idempotence
+of order_columns.
+"""
+
+import numpy as np
+import pytest
+
+from csr_b200 import CSR, synth
+from csr_b200.dist import partition_rows
+from oracle import oracle as orc
+from util import canonical, assert_values_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _mv_scale(A, x):
+    vmax = 1.0 if A.values is None else float(np.abs(A.values).max(initial=0.0))
+    return vmax * float(np.abs(x).max(initial=0.0)) * float(np.diff(A.rowptrs).max(initial=1)) ** 0.5
+
+
+@pytest.mark.parametrize("dtype,xdt,rp64", [("f4", "f4", False), ("f8", "f8", False), ("f4", "f8", True),
+                                            ("f8", "f4", False), (None, "f4", False), (None, "f8", True)])
+def test_spmv_powerlaw(kernel, dtype, xdt, rp64):
+    # 300k nnz, rows from length 0.. to a 60k-entry row spanning 15 tiles
+    A = synth.powerlaw_csr(4000, 60000, 300000, seed=21, dtype=dtype or "f4", alpha=1.0, values=dtype is not None)
+    if rp64:
+        A = CSR(A.nrows, A.ncols, A.nnz, A.rowptrs.astype(np.int64), A.colinds, A.values, _cast=False)
+    x = synth.dense_vector(A.ncols, 22, xdt)
+    h = kernel.to_handle(A)
+    try:
+        y = kernel.mult_vec(h, x)
+        y2 = kernel.mult_vec(h, x)
+    finally:
+        kernel.release_handle(h)
+    ref = orc.mult_vec(A, x)
+    f4 = dtype == "f4" or xdt == "f4"
+    assert_values_close(y, ref, 1e-5 if f4 else 1e-10, _mv_scale(A, x))
+    assert np.array_equal(y, y2), "mult_vec must be deterministic (no float atomics)"
+
+
+def test_spmv_empty_rows_and_tile_edges(kernel):
+    # nnz an exact multiple of the 4096-entry tile, leading/trailing/inner empty rows
+    rng = np.random.default_rng(5)
+    lens = np.zeros(3000, np.int64)
+    lens[rng.choice(3000, 1024, replace=False)] = 16      # 16384 nnz = 4 tiles exactly
+    lens[0] = lens[-1] = lens[-2] = 0
+    lens[1500] += 16 - lens[1500]
+    lens[rng.integers(3, 2990)] += 16384 - lens.sum()
+    cols = synth.stratified_columns(lens, 5000, rng)
+    rp = np.zeros(3001, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    A = CSR(3000, 5000, int(rp[-1]), rp, cols, rng.normal(size=int(rp[-1])))
+    assert A.nnz % 4096 == 0
+    x = rng.normal(size=5000)
+    y = A.mult_vec(x)
+    assert_values_close(y, orc.mult_vec(A, x), 1e-10, _mv_scale(A, x))
+    assert np.all(y[lens == 0] == 0.0)
+
+
+def test_spmv_linearity(kernel):
+    A = synth.powerlaw_csr(2000, 3000, 100000, seed=31, dtype="f8", alpha=0.8)
+    x1, x2 = synth.dense_vector(3000, 1, "f8"), synth.dense_vector(3000, 2, "f8")
+    h = kernel.to_handle(A)
+    try:
+        y1, y2, y12 = kernel.mult_vec(h, x1), kernel.mult_vec(h, x2), kernel.mult_vec(h, 2.0 * x1 - x2)
+    finally:
+        kernel.release_handle(h)
+    assert_values_close(y12, 2.0 * y1 - y2, 1e-10, _mv_scale(A, np.abs(x1) * 2 + np.abs(x2)))
+
+
+@pytest.mark.parametrize("shape,nnz,dtype", [((3000, 2000), 150000, "f8"), ((500, 70000), 120000, "f4"),
+                                            ((70000, 300), 200000, "f8"), ((2000, 2000), 0, "f8")])
+def test_transpose_large(kernel, shape, nnz, dtype):
+    A = synth.powerlaw_csr(shape[0], shape[1], nnz, seed=41, dtype=dtype, alpha=0.9)
+    h = kernel.to_handle(A)
+    try:
+        th = kernel.transpose(h)
+        T = kernel.from_handle(th)
+        tth = kernel.transpose(th)
+        TT = kernel.from_handle(tth)
+        kernel.release_handle(th)
+        kernel.release_handle(tth)
+    finally:
+        kernel.release_handle(h)
+    R = orc.transpose(A)
+    assert np.array_equal(T.rowptrs, R.rowptrs) and np.array_equal(T.colinds, R.colinds)
+    assert np.array_equal(T.values, R.values)
+    # (A^T)^T == A exactly (columns were sorted and unique); values widened to float64
+    assert np.array_equal(TT.rowptrs, A.rowptrs) and np.array_equal(TT.colinds, A.colinds)
+    assert np.array_equal(TT.values, A.values.astype(np.float64))
+
+
+def test_order_columns_large_and_idempotent(kernel):
+    rng = np.random.default_rng(8)
+    A = synth.powerlaw_csr(3000, 50000, 200000, seed=42, dtype="f4", alpha=1.0)
+    # shuffle the entries inside every row
+    rows = np.repeat(np.arange(A.nrows), np.diff(A.rowptrs))
+    perm = np.lexsort((rng.random(A.nnz), rows))
+    S = CSR(A.nrows, A.ncols, A.nnz, A.rowptrs, A.colinds[perm], A.values[perm])
+    h = kernel.to_handle(S)
+    try:
+        kernel.order_columns(h)
+        got = kernel.from_handle(h)
+        kernel.order_columns(h)
+        again = kernel.from_handle(h)
+    finally:
+        kernel.release_handle(h)
+    assert np.array_equal(got.colinds, A.colinds) and np.array_equal(got.values, A.values)
+    assert np.array_equal(again.colinds, got.colinds) and np.array_equal(again.values, got.values)
+
+
+def _check_mm(kernel, A, B, tr, rtol):
+    ref = orc.mult_abt(A, B) if tr else orc.mult_ab(A, B)
+    rp, ci, vs = canonical(ref)
+    ah, bh = kernel.to_handle(A), kernel.to_handle(B)
+    try:
+        ch = kernel.mult_abt(ah, bh) if tr else kernel.mult_ab(ah, bh)
+        got = kernel.from_handle(ch)
+        st = kernel.spgemm_stats(ch)
+        kernel.release_handle(ch)
+    finally:
+        kernel.release_handle(ah)
+        kernel.release_handle(bh)
+    assert got.rowptrs.dtype == np.int32 and np.array_equal(got.rowptrs, rp)
+    assert np.array_equal(got.colinds, ci)
+    scale = float(np.abs(A.values).max() * np.abs(B.values).max()) * float(np.diff(A.rowptrs).max()) ** 0.5
+    assert_values_close(got.values, vs, rtol, scale)
+    assert st["out_nnz"] == ref.nnz
+    return got, st
+
+
+def test_spgemm_all_bins(kernel):
+    """Row lengths from 0 to thousands so every symbolic bin (warp / CTA 4k / CTA 32k /
+    bitmap) and every numeric bin (warp / CTA 2k / CTA 16k / dense) is exercised."""
+    A = synth.powerlaw_csr(1500, 4000, 30000, seed=51, dtype="f8", alpha=1.5)
+    B = synth.powerlaw_csr(4000, 30000, 150000, seed=52, dtype="f8", alpha=1.2)
+    got, st = _check_mm(kernel, A, B, False, 1e-10)
+    nz = np.diff(got.rowptrs)
+    hist = np.histogram(nz, [0, 1, 65, 1025, 8193, 10 ** 9])[0]
+    assert np.all(hist > 0), f"a numeric bin was not exercised: {hist}"
+    assert st["products"] >= st["out_nnz"]
+
+
+def test_spgemm_wide_global_scratch(kernel):
+    "B.ncols too large for the shared-memory bitmap / dense accumulator: global scratch paths."
+    A = synth.powerlaw_csr(300, 2000, 40000, seed=53, dtype="f8", alpha=1.2)
+    B = synth.powerlaw_csr(2000, 2_000_000, 300000, seed=54, dtype="f8", alpha=0.5)
+    _check_mm(kernel, A, B, False, 1e-10)
+
+
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
+def test_item_item_abt(kernel, dtype):
+    "configs[2] shape, scaled: M = ratings^T, M M^T"
+    R = synth.cfg3_ratings(0.02)
+    if dtype == "f4":
+        R = CSR(R.nrows, R.ncols, R.nnz, R.rowptrs, R.colinds, R.values.astype(np.float32))
+    M = R.transpose()          # float64 values either way (structure.py:177)
+    assert M.values.dtype == np.float64
+    _check_mm(kernel, M, M, True, 1e-10)
+
+
+def test_virtual_ranks_row_blocks(kernel):
+    """N ranks emulated as N row shards on one GPU; the concatenation equals
+    the unsharded result (structure exactly; values up to atomic ordering)."""
+    A = synth.powerlaw_csr(3000, 2500, 90000, seed=61, dtype="f8", alpha=1.0)
+    B = synth.powerlaw_csr(2500, 3500, 80000, seed=62, dtype="f8", alpha=0.8)
+    x = synth.dense_vector(2500, 63, "f8")
+    full = A.multiply(B)
+    yfull = A.mult_vec(x)
+    for n in (2, 4, 8):
+        cuts = partition_rows(A.rowptrs, n)
+        shards = [A.subset_rows(cuts[i], cuts[i + 1]) for i in range(n)]
+        parts = [s.multiply(B) for s in shards]
+        C = CSR._assemble_shards(parts)
+        assert np.array_equal(C.rowptrs, full.rowptrs) and np.array_equal(C.colinds, full.colinds)
+        assert_values_close(C.values, full.values, 1e-12, float(np.abs(full.values).max()))
+        y = np.concatenate([s.mult_vec(x) for s in shards])
+        assert_values_close(y, yfull, 1e-12, _mv_scale(A, x))
+        # the same through device-side row slices of one resident handle
+        h = kernel.to_handle(A)
+        try:
+            ys = []
+            for i in range(n):
+                sh = kernel.subset_rows(h, cuts[i], cuts[i + 1])
+                ys.append(kernel.mult_vec(sh, x))
+                kernel.release_handle(sh)
+        finally:
+            kernel.release_handle(h)
+        assert_values_close(np.concatenate(ys), yfull, 1e-12, _mv_scale(A, x))
+
+
+def test_structure_only_product(kernel):
+    "Superset of the numba kernel (which cannot type value-less inputs): values count as 1, like the MKL kernel."
+    A = synth.powerlaw_csr(200, 300, 4000, seed=71, dtype="f8", values=False)
+    B = synth.powerlaw_csr(300, 250, 5000, seed=72, dtype="f8", values=False)
+    ones = lambda m: CSR(m.nrows, m.ncols, m.nnz, m.rowptrs, m.colinds, np.ones(m.nnz))
+    ref = canonical(orc.mult_ab(ones(A), ones(B)))
+    ah, bh = kernel.to_handle(A), kernel.to_handle(B)
+    ch = kernel.mult_ab(ah, bh)
+    got = kernel.from_handle(ch)
+    for hh in (ah, bh, ch):
+        kernel.release_handle(hh)
+    assert np.array_equal(got.rowptrs, ref[0]) and np.array_equal(got.colinds, ref[1])
+    assert np.array_equal(got.values, ref[2])     # small integer counts: exact
+
+
+def test_released_handle_is_rejected(kernel):
+    h = kernel.to_handle(CSR.empty(3, 3))
+    kernel.release_handle(h)
+    kernel.release_handle(h)           # second release is a no-op, like mkl_h
+    with pytest.raises(ValueError):
+        kernel.mult_vec(h, np.zeros(3))
+
+
+def test_shape_errors(kernel):
+    a = kernel.to_handle(CSR.empty(3, 4))
+    b = kernel.to_handle(CSR.empty(5, 6))
+    try:
+        with pytest.raises(AssertionError):
+            kernel.mult_ab(a, b)         # multiply.py:26
+        with pytest.raises(AssertionError):
+            kernel.mult_abt(a, b)        # multiply.py:53
+        with pytest.raises(ValueError):
+            kernel.mult_vec(a, np.zeros(3))
+    finally:
+        kernel.release_handle(a)
+        kernel.release_handle(b)

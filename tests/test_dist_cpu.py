@@ -1,0 +1,103 @@
+"""
+CPU, world_size 2 on the gloo backend: the host-side logic of the row-partitioned
+multi-GPU layer (csr_b200/dist.py) -- nnz-balanced partition, x broadcast, padded
+all-gather of y segments, replication of B, and block assembly with the rowptr
+fix-up of CSR._assemble_shards (csr/csr.py:623-650).
+
+The local compute is injected and is the ORACLE here (tests may use it); on a GPU
+box the same layer runs the cuda kernel (tests/test_cuda_dist.py, bench.py).
+"""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from csr_b200 import CSR, synth
+        from csr_b200.dist import DistSpMV, partition_rows, replicate_csr, dist_multiply, assemble_blocks
+        from oracle import oracle as orc
+
+        # every rank builds the same global matrix, keeps its own row block
+        A = synth.powerlaw_csr(700, 500, 20000, seed=5, dtype="f8", alpha=1.0)
+        cuts = partition_rows(A.rowptrs, world)
+        mine = A.subset_rows(cuts[rank], cuts[rank + 1])
+        counts = [cuts[r + 1] - cuts[r] for r in range(world)]
+
+        def compute(x, y):  # oracle-backed local SpMV writing into the gather segment
+            y.copy_(torch.from_numpy(orc.mult_vec(mine, x.numpy())))
+
+        ds = DistSpMV(mine, counts, x_dtype="f8", device=torch.device("cpu"), compute=compute)
+        x = np.random.default_rng(9).standard_normal(A.ncols)
+        if rank == 0:
+            ds.set_x(x)          # only the root has x; step() broadcasts it
+        ds.step()
+        y = ds.result()
+        ref = orc.mult_vec(A, x)
+        ok_spmv = bool(np.array_equal(y, ref))
+
+        # SpGEMM: B known on rank 0 only, replicated by broadcast; A row blocks; assemble
+        B = synth.powerlaw_csr(500, 300, 6000, seed=6, dtype="f8", alpha=0.7) if rank == 0 else None
+        Brep = replicate_csr(B, src=0, device=torch.device("cpu"))
+
+        def mul(a, b, tr):
+            m = orc.canonical(orc.mult_abt(a, b) if tr else orc.mult_ab(a, b))
+            return CSR(m.nrows, m.ncols, m.nnz, m.rowptrs, m.colinds, m.values)
+
+        Cloc = dist_multiply(mine, Brep, multiply=mul)
+        C = assemble_blocks(Cloc, device=torch.device("cpu"))
+        Bfull = synth.powerlaw_csr(500, 300, 6000, seed=6, dtype="f8", alpha=0.7)
+        Cref = orc.canonical(orc.mult_ab(A, Bfull))
+        ok_mm = (C.nnz == Cref.nnz and np.array_equal(C.rowptrs, Cref.rowptrs)
+                 and np.array_equal(C.colinds, Cref.colinds) and np.array_equal(C.values, Cref.values))
+        ok_rep = (Brep.nnz == Bfull.nnz and np.array_equal(Brep.colinds, Bfull.colinds)
+                  and np.array_equal(Brep.values, Bfull.values) and Brep.rowptrs.dtype == Bfull.rowptrs.dtype)
+        q.put((rank, ok_spmv, ok_mm, ok_rep, counts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_rows_balanced():
+    sys.path.insert(0, ROOT)
+    from csr_b200 import synth
+    from csr_b200.dist import partition_rows
+    A = synth.powerlaw_csr(5000, 4000, 200000, seed=1, dtype="f4", alpha=1.0)
+    for n in (1, 2, 4, 8):
+        cuts = partition_rows(A.rowptrs, n)
+        assert cuts[0] == 0 and cuts[-1] == A.nrows and len(cuts) == n + 1
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        nnzs = np.diff(A.rowptrs[cuts])
+        longest = np.diff(A.rowptrs).max()
+        assert nnzs.max() <= A.nnz / n + longest      # balanced up to one row
+
+
+def test_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, ok_spmv, ok_mm, ok_rep, counts in res:
+        assert ok_spmv, f"rank {rank}: distributed SpMV differs from the unsharded result"
+        assert ok_mm, f"rank {rank}: assembled SpGEMM differs from the unsharded result"
+        assert ok_rep, f"rank {rank}: replicated B differs"
+        assert sum(counts) == 700
