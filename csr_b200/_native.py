@@ -29,6 +29,7 @@ SIGNATURES = {
     "csrk_device_info": (_int, [_P(_int), _P(_i64), _P(_i64), _P(_int), _P(_int)]),
     "csrk_launch_count": (_i64, []),
     "csrk_synchronize": (_int, []),
+    "csrk_set_option": (_int, [C.c_char_p, _i64]),
     "csrk_get_stream": (_int, [_P(_vp)]),
     "csrk_create": (_int, [_i32, _i32, _i64, _vp, _int, _vp, _vp, _int, _P(_vp)]),
     "csrk_create_dev": (_int, [_i32, _i32, _i64, _vp, _int, _vp, _vp, _int, _vp, _P(_vp)]),

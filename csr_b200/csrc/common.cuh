@@ -91,7 +91,15 @@ int dev_alloc(void **p, size_t bytes, cudaStream_t s);
 void dev_free(void *p, cudaStream_t s);
 
 // ------------------------------------------------------------------ matrix
-struct SpmvPlan;  // spmv.cu
+struct SpmvPlan;  // spmv.cu: tile map of the CSR kernel
+struct PsfPlan;   // spmv_psf.cu: panel/slab re-layout for large matrices
+
+// tunables settable through csrk_set_option (tests force the slab path on small inputs)
+struct Options {
+    std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab kernel
+    std::atomic<int64_t> psf_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a slab plan
+};
+Options &options();
 
 }  // namespace csrk
 
@@ -106,6 +114,8 @@ struct csrk_matrix {
     int val_kind = 0;       // 0, 4, 8
     int64_t stat_products = -1, stat_out_nnz = -1;
     csrk::SpmvPlan *plan = nullptr;  // lazily built SpMV tile map
+    csrk::PsfPlan *psf[2] = {nullptr, nullptr};  // lazily built slab plans for float32 / float64 x
+    bool psf_failed[2] = {false, false};
     std::mutex mu;
 };
 
@@ -116,6 +126,10 @@ int matrix_alloc(csrk_matrix **out, int32_t nrows, int32_t ncols, int64_t nnz, i
 void matrix_destroy(csrk_matrix *m, cudaStream_t s);
 void plan_destroy(SpmvPlan *p, cudaStream_t s);
 void plan_invalidate(csrk_matrix *m, cudaStream_t s);
+void psf_destroy(PsfPlan *p, cudaStream_t s);
+int psf_build(csrk_matrix *h, int x_kind, PsfPlan **out, cudaStream_t s);  // syncs internally
+int psf_run(csrk_matrix *h, PsfPlan *p, const void *d_x, double *d_y, cudaStream_t s);
+int psf_panels(const PsfPlan *p);
 
 // ops implemented across the .cu files (all enqueue on `s`, no sync unless stated)
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s);
@@ -160,6 +174,26 @@ __device__ __forceinline__ double2 ld_stream_double2(const void *ptr)
 {
     double2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(ptr));
+    return r;
+}
+
+__device__ __forceinline__ int ld_stream_i32(const int *ptr)
+{
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(ptr));
+    return r;
+}
+template <typename T> __device__ __forceinline__ T ld_stream(const T *ptr);
+template <> __device__ __forceinline__ float ld_stream<float>(const float *ptr)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(ptr));
+    return r;
+}
+template <> __device__ __forceinline__ double ld_stream<double>(const double *ptr)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(ptr));
     return r;
 }
 

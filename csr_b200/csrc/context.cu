@@ -39,6 +39,12 @@ Context &ctx()
     return c;
 }
 
+Options &options()
+{
+    static Options o;
+    return o;
+}
+
 static int init_locked(Context &c, int device)
 {
     if (c.inited) {
@@ -168,6 +174,8 @@ void matrix_destroy(csrk_matrix *m, cudaStream_t s)
     dev_free(m->ci, s);
     dev_free(m->vs, s);
     plan_destroy(m->plan, s);
+    psf_destroy(m->psf[0], s);
+    psf_destroy(m->psf[1], s);
     delete m;
 }
 
@@ -176,6 +184,11 @@ void plan_invalidate(csrk_matrix *m, cudaStream_t s)
     std::lock_guard<std::mutex> g(m->mu);
     plan_destroy(m->plan, s);
     m->plan = nullptr;
+    for (int k = 0; k < 2; k++) {
+        psf_destroy(m->psf[k], s);
+        m->psf[k] = nullptr;
+        m->psf_failed[k] = false;
+    }
 }
 
 static int check_shape(int32_t nrows, int32_t ncols, int64_t nnz, int rp_is64, int val_kind)
@@ -239,6 +252,21 @@ int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *
 }
 
 int64_t csrk_launch_count(void) { return g_launches.load(); }
+
+int csrk_set_option(const char *name, int64_t value)
+{
+    CSRK_ARG(name != nullptr, "option name is NULL");
+    if (!strcmp(name, "spmv_mode")) {
+        CSRK_ARG(value >= 0 && value <= 2, "spmv_mode must be 0 (auto), 1 (tile) or 2 (slab)");
+        options().spmv_mode = value;
+    } else if (!strcmp(name, "psf_min_nnz")) {
+        options().psf_min_nnz = value;
+    } else {
+        set_error("unknown option `%s`", name);
+        return CSRK_EARG;
+    }
+    return CSRK_OK;
+}
 
 int csrk_get_stream(void **stream)
 {

@@ -75,21 +75,6 @@ __global__ void k_zero_f64(double *y, int64_t n)
         y[i] = 0.0;
 }
 
-template <typename VT> struct ValLoad4 {
-    // four consecutive values starting at element index e (multiple of 4), as doubles or floats
-    __device__ static __forceinline__ void load(const VT *vs, int64_t e, VT (&v)[4]);
-};
-template <> __device__ __forceinline__ void ValLoad4<float>::load(const float *vs, int64_t e, float (&v)[4])
-{
-    float4 f = ld_stream_float4(vs + e);
-    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-}
-template <> __device__ __forceinline__ void ValLoad4<double>::load(const double *vs, int64_t e, double (&v)[4])
-{
-    double2 a = ld_stream_double2(vs + e), b = ld_stream_double2(vs + e + 2);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
 template <typename RPT, typename VT, typename XT>
 __global__ void __launch_bounds__(SPMV_BLOCK)
 k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_t *__restrict__ ci,
@@ -112,35 +97,28 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
         q_n = 0;
 
     // ---- phase 1: stream + gather + multiply
+    // Lane i of a warp takes entry 32k+i: ADJACENT LANES HOLD ADJACENT ENTRIES.  The x gather is
+    // bound by the L1 tag stage (one 128-byte line per cycle per SM, profiles/r01_spmv_v1_ncu.md),
+    // and in a long row consecutive entries are a few columns apart, so a warp-wide gather then
+    // touches C/L lines instead of 32.  The index/value streams are fully coalesced 128-byte
+    // warp loads (no L1 allocation); all of a thread's loads are issued before the first gather.
     if (cnt == SPMV_TILE) {
-        int4 c[SPMV_ITEMS / 4];
-        RV v[SPMV_ITEMS / 4][4];
+        int c[SPMV_ITEMS];
+        RV v[SPMV_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SPMV_ITEMS / 4; k++) {
-            const int64_t e = base + 4 * (k * SPMV_BLOCK + tid);
-            c[k] = ld_stream_int4(ci + e);
+        for (int k = 0; k < SPMV_ITEMS; k++) {
+            const int64_t e = base + k * SPMV_BLOCK + tid;
+            c[k] = ld_stream_i32(ci + e);
             if constexpr (HASV)
-                ValLoad4<RV>::load(reinterpret_cast<const RV *>(vs), e, v[k]);
+                v[k] = ld_stream<RV>(reinterpret_cast<const RV *>(vs) + e);
         }
 #pragma unroll
-        for (int k = 0; k < SPMV_ITEMS / 4; k++) {
-            XT x0 = __ldg(x + c[k].x), x1 = __ldg(x + c[k].y), x2 = __ldg(x + c[k].z), x3 = __ldg(x + c[k].w);
-            PT p0, p1, p2, p3;
-            if constexpr (HASV) {
-                p0 = (PT)x0 * (PT)v[k][0];
-                p1 = (PT)x1 * (PT)v[k][1];
-                p2 = (PT)x2 * (PT)v[k][2];
-                p3 = (PT)x3 * (PT)v[k][3];
-            } else {
-                p0 = (PT)x0; p1 = (PT)x1; p2 = (PT)x2; p3 = (PT)x3;
-            }
-            PT *dst = prod + 4 * (k * SPMV_BLOCK + tid);
-            if constexpr (sizeof(PT) == 4) {
-                *reinterpret_cast<float4 *>(dst) = make_float4(p0, p1, p2, p3);
-            } else {
-                *reinterpret_cast<double2 *>(dst) = make_double2(p0, p1);
-                *reinterpret_cast<double2 *>(dst + 2) = make_double2(p2, p3);
-            }
+        for (int k = 0; k < SPMV_ITEMS; k++) {
+            const XT xv = __ldg(x + c[k]);
+            if constexpr (HASV)
+                prod[k * SPMV_BLOCK + tid] = (PT)xv * (PT)v[k];
+            else
+                prod[k * SPMV_BLOCK + tid] = (PT)xv;
         }
     } else {
         for (int i = tid; i < cnt; i += SPMV_BLOCK) {
@@ -302,6 +280,38 @@ static int launch_spmv_v(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kin
     }
 }
 
+// The panel/slab kernel (spmv_psf.cu) is opt-in ("spmv_mode" = 2): measured on B200 at
+// 1M x 1M / 100M nnz it is still slower than the CSR tile kernel (0.50 ms vs 0.36 ms,
+// profiles/r01_spmv_psf_ncu.md: issue-bound segmented reduction on half-empty blocks plus
+// one exposed HBM latency per slab step), so auto mode stays on the tile kernel.
+static bool psf_wanted(const csrk_matrix *h, int x_kind, const void *d_x)
+{
+    if (options().spmv_mode.load() != 2 || ((uintptr_t)d_x & 15) != 0)  // TMA bulk copies need 16-byte aligned x
+        return false;
+    const int64_t nslabs = div_up((int64_t)h->ncols * x_kind, 64 * 1024);
+    return nslabs <= 4096 && h->nnz < ((int64_t)1 << 33);
+}
+
+static int ensure_psf(csrk_matrix *h, int x_kind, PsfPlan **out)
+{
+    const int k = x_kind == 4 ? 0 : 1;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->psf[k] && !h->psf_failed[k]) {
+        PsfPlan *p = nullptr;
+        const int rc = psf_build(h, x_kind, &p, ctx().stream);
+        if (rc == CSRK_EOVERFLOW) {
+            h->psf_failed[k] = true;  // not representable: stay on the CSR kernel
+            return CSRK_OK;
+        }
+        if (rc != CSRK_OK)
+            return rc;
+        h->psf[k] = p;
+    }
+    *out = h->psf[k];
+    return CSRK_OK;
+}
+
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s)
 {
     if (h->nrows == 0)
@@ -309,6 +319,12 @@ int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStrea
     if (h->nnz == 0) {
         CSRK_LAUNCH(k_zero_f64, (unsigned)div_up(h->nrows, 256), 256, 0, s, d_y, (int64_t)h->nrows);
         return CSRK_OK;
+    }
+    if (psf_wanted(h, x_kind, d_x)) {
+        PsfPlan *pp = nullptr;
+        CSRK_TRY(ensure_psf(h, x_kind, &pp));
+        if (pp)
+            return psf_run(h, pp, d_x, d_y, s);
     }
     SpmvPlan *p = nullptr;
     CSRK_TRY(ensure_plan(h, ctx().stream, &p));

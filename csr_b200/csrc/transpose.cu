@@ -15,98 +15,9 @@
 // order_columns is the same machinery applied twice: (A^T)^T with both counting
 // sorts stable leaves every row sorted by column with equal columns in their
 // original relative order -- exactly what the reference's bubble sort produces.
-#include <type_traits>
-
-#include "common.cuh"
-#include "scan.cuh"
+#include "radix.cuh"
 
 namespace csrk {
-
-constexpr int RS_BLOCK = 256;
-constexpr int RS_WARPS = RS_BLOCK / 32;
-constexpr int RS_STEPS = 16;
-constexpr int RS_TILE = RS_BLOCK * RS_STEPS;  // 4096 entries per CTA
-constexpr int RS_WARP_ITEMS = 32 * RS_STEPS;
-
-struct NoPayload {};
-
-__global__ void __launch_bounds__(RS_BLOCK)
-k_radix_hist(const int32_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ tile_hist, int64_t ntiles)
-{
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
-    for (int k = 0; k < RS_STEPS; k++) {
-        int64_t i = base + (int64_t)k * RS_BLOCK + threadIdx.x;
-        if (i < n)
-            atomicAdd(&h[(keys[i] >> shift) & 255], 1u);
-    }
-    __syncthreads();
-    tile_hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
-}
-
-template <typename VT>
-__global__ void __launch_bounds__(RS_BLOCK)
-k_radix_scatter(const int32_t *__restrict__ keys_in, const int32_t *__restrict__ rows_in, const VT *__restrict__ vals_in,
-                int32_t *__restrict__ keys_out, int32_t *__restrict__ rows_out, VT *__restrict__ vals_out, int64_t n,
-                int shift, const int64_t *__restrict__ tile_off, int64_t ntiles)
-{
-    __shared__ uint32_t wc[RS_WARPS][256];
-    __shared__ int64_t toff[256];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < RS_WARPS; k++)
-        wc[k][tid] = 0;
-    toff[tid] = tile_off[(int64_t)tid * ntiles + blockIdx.x];
-    __syncthreads();
-
-    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_ITEMS;
-    int32_t key[RS_STEPS];
-    uint32_t rank[RS_STEPS];
-    const unsigned lt = lanemask_lt();
-#pragma unroll
-    for (int k = 0; k < RS_STEPS; k++) {
-        const int64_t i = wbase + k * 32 + lane;
-        const bool valid = i < n;
-        key[k] = valid ? keys_in[i] : 0;
-        // invalid lanes get a unique pseudo-digit so they match nobody
-        const unsigned d = valid ? (unsigned)((key[k] >> shift) & 255) : 256u + lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned before = __popc(peers & lt);
-        const uint32_t cur = valid ? wc[w][d] : 0u;
-        __syncwarp();
-        if (valid && before == 0)
-            wc[w][d] = cur + __popc(peers);
-        __syncwarp();
-        rank[k] = cur + before;
-    }
-    __syncthreads();
-    {
-        // exclusive prefix over the warps for digit `tid`
-        uint32_t run = 0;
-#pragma unroll
-        for (int k = 0; k < RS_WARPS; k++) {
-            uint32_t c = wc[k][tid];
-            wc[k][tid] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RS_STEPS; k++) {
-        const int64_t i = wbase + k * 32 + lane;
-        if (i < n) {
-            const unsigned d = (unsigned)((key[k] >> shift) & 255);
-            const int64_t pos = toff[d] + wc[w][d] + rank[k];
-            keys_out[pos] = key[k];
-            rows_out[pos] = rows_in[i];
-            if constexpr (!std::is_same<VT, NoPayload>::value)
-                vals_out[pos] = vals_in[i];
-        }
-    }
-}
 
 // rows[i] = the row that owns nnz position i (last r with rp[r] <= i)
 template <typename RPT>
@@ -191,38 +102,9 @@ static int transpose_core(int32_t nrows, int32_t ncols, int64_t nnz, const RPT *
     CSRK_TRY(rows0.alloc(sizeof(int32_t) * (size_t)nnz, s));
     CSRK_LAUNCH((k_expand_rows<RPT>), (unsigned)div_up(nnz, 256), 256, 0, s, rp, nrows, nnz, rows0.as<int32_t>());
 
-    // 3. LSD radix passes, ping-pong; the last pass lands in out.ci / out.vs
-    const int npass = (key_bits(ncols) + 7) / 8;
-    const int64_t ntiles = div_up(nnz, RS_TILE);
-    DevBuf keysA, keysB, rowsT, valsT, hist, offs;
-    CSRK_TRY(keysA.alloc(sizeof(int32_t) * (size_t)nnz, s));
-    if (npass > 1) {
-        CSRK_TRY(keysB.alloc(sizeof(int32_t) * (size_t)nnz, s));
-        CSRK_TRY(rowsT.alloc(sizeof(int32_t) * (size_t)nnz, s));
-        if (HASV)
-            CSRK_TRY(valsT.alloc(sizeof(VT) * (size_t)nnz, s));
-    }
-    CSRK_TRY(hist.alloc(sizeof(uint32_t) * 256 * (size_t)ntiles, s));
-    CSRK_TRY(offs.alloc(sizeof(int64_t) * (256 * (size_t)ntiles + 1), s));
-
-    const int32_t *kin = ci;
-    const int32_t *rin = rows0.as<int32_t>();
-    const VT *vin = vs;
-    for (int pass = 0; pass < npass; pass++) {
-        // choose destinations so that the final pass writes the outputs
-        const bool to_out = ((npass - 1 - pass) % 2) == 0;
-        int32_t *kout = (pass % 2 == 0) ? keysA.as<int32_t>() : keysB.as<int32_t>();
-        int32_t *rout = to_out ? out.ci.as<int32_t>() : rowsT.as<int32_t>();
-        VT *vout = HASV ? (to_out ? out.vs.as<VT>() : valsT.as<VT>()) : nullptr;
-        const int shift = 8 * pass;
-        CSRK_LAUNCH(k_radix_hist, (unsigned)ntiles, RS_BLOCK, 0, s, kin, nnz, shift, hist.as<uint32_t>(), ntiles);
-        CSRK_TRY((exclusive_scan<int64_t>(ArrayLoader<uint32_t>{hist.as<uint32_t>()}, 256 * ntiles, offs.as<int64_t>(), s)));
-        CSRK_LAUNCH((k_radix_scatter<VT>), (unsigned)ntiles, RS_BLOCK, 0, s, kin, rin, vin, kout, rout, vout, nnz, shift,
-                    offs.as<int64_t>(), ntiles);
-        kin = kout;
-        rin = rout;
-        vin = vout;
-    }
+    // 3. stable LSD radix sort by column; the payloads land in out.ci / out.vs
+    CSRK_TRY((radix_sort_by_key<VT>(ci, rows0.as<int32_t>(), vs, nnz, key_bits(ncols), out.ci.as<int32_t>(),
+                                    HASV ? out.vs.as<VT>() : nullptr, s)));
     return CSRK_OK;
 }
 

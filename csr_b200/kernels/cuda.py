@@ -237,6 +237,12 @@ def from_device_arrays(nrows, ncols, nnz, rowptrs_ptr, rp_is64, colinds_ptr, val
     return cuda_h(out.value, nrows, ncols, nnz, csr_cls)
 
 
+def set_option(name: str, value: int) -> None:
+    """Library tunables: ``spmv_mode`` (0 auto, 1 CSR tile kernel, 2 panel/slab kernel),
+    ``psf_min_nnz`` (smallest nnz for which auto mode builds a slab plan)."""
+    N.check(N.lib().csrk_set_option(name.encode(), int(value)), "set_option")
+
+
 def library_stream() -> int:
     "The library's own stream as an integer cudaStream_t."
     out = C.c_void_p()

@@ -126,12 +126,13 @@ def cfg2_spmv(scale: float = 1.0, col_skew: float = 1.0, seed: int = 2, dtype="f
 def cfg3_ratings(scale: float = 1.0) -> CSR:
     """100k users x 50k items, 20M nnz, float64.  Item-item similarity is
     ``M.multiply(M, transpose=True)`` with ``M = ratings.transpose()``.  User lengths
-    are capped and item popularity is mildly skewed so that out-nnz < 2**31."""
+    are capped and item popularity is skewed (t**3 strata) so that out-nnz stays below 2**31
+    (measured: Z = 1.6e9, 65 % dense, P = 7.3e9 products at full scale)."""
     nu, ni = max(int(100_000 * scale), 16), max(int(50_000 * scale), 16)
     nnz = min(200 * nu, nu * ni // 4)
     mean = max(nnz // nu, 1)
     return powerlaw_csr(nu, ni, nnz, seed=3, dtype="f8", alpha=0.5,
-                        cap=max(ni // 25, min(ni, 4 * mean)), min_len=min(20, mean // 2), col_skew=1.5)
+                        cap=max(ni // 25, min(ni, 4 * mean)), min_len=min(20, mean // 2), col_skew=3.0)
 
 
 def cfg4_square(scale: float = 1.0, dtype="f8") -> CSR:

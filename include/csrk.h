@@ -61,6 +61,9 @@ int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t csrk_launch_count(void);
 int csrk_synchronize(void);
+/* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 panel/slab kernel;
+ * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan. */
+int csrk_set_option(const char *name, int64_t value);
 /* the library's own (non-blocking) stream, as a cudaStream_t */
 int csrk_get_stream(void **stream);
 
