@@ -98,6 +98,7 @@ struct PsfPlan;   // spmv_psf.cu: panel/slab re-layout for large matrices
 struct Options {
     std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab kernel
     std::atomic<int64_t> psf_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a slab plan
+    std::atomic<int64_t> own_nw{16};                    // warps (column ranges) per CTA in the owner-computes SpGEMM
 };
 Options &options();
 

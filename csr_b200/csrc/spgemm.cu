@@ -43,7 +43,7 @@ static MatView view(const csrk_matrix *m)
     return MatView{m->nrows, m->ncols, m->nnz, m->rp, m->rp_is64, m->ci, m->vs, m->val_kind};
 }
 
-constexpr int NBINS = 5;
+constexpr int NBINS = 6;
 struct BinSpec {
     int64_t upper[NBINS];  // value <= upper[b] -> bin b (first match); last is INT64_MAX
 };
@@ -57,7 +57,7 @@ __device__ __forceinline__ unsigned hash_col(int32_t k, unsigned mask)
 
 __device__ __forceinline__ double product(double av, double bv, int both_f32)
 {
-    return both_f32 ? (double)((float)av * (float)bv) : av * bv;
+    return both_f32 ? (double)__fmul_rn((float)av, (float)bv) : __dmul_rn(av, bv);
 }
 
 // ------------------------------------------------------------ step 0: products
@@ -202,11 +202,14 @@ __global__ void __launch_bounds__(THREADS) k_sym_cta(MatView A, MatView B, const
 // ------------------------------------------------- symbolic: bitmap (heavy rows)
 // Persistent CTAs pull rows from a counter.  The column bitmap lives in shared
 // memory when SMEM_BM, else in this CTA's slice of a zero-initialised global
-// scratch; either way it is restored to zero while it is counted.
+// scratch; either way it is restored to zero while it is counted.  When `keep` is
+// given, the row's bitmap is also stored there (slot = position in the bin) so the
+// numeric phase does not have to rebuild it: keep_slot[row] = slot.
 template <bool SMEM_BM, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin,
                                                         int32_t *__restrict__ row_nnz, unsigned *__restrict__ gbm,
-                                                        int n_words, int *__restrict__ work_counter)
+                                                        int n_words, int *__restrict__ work_counter,
+                                                        unsigned *__restrict__ keep, int32_t *__restrict__ keep_slot)
 {
     extern __shared__ unsigned s_bm[];
     __shared__ int s_idx, s_count;
@@ -238,8 +241,11 @@ __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, co
         }
         __syncthreads();
         int count = 0;
+        unsigned *dst = keep ? keep + (size_t)idx * n_words : nullptr;
         for (int i = tid; i < n_words; i += THREADS) {
             const unsigned bits = SMEM_BM ? bm[i] : __ldcg(&bm[i]);
+            if (dst)
+                dst[i] = bits;
             if (bits) {
                 count += __popc(bits);
                 if (SMEM_BM)
@@ -252,8 +258,11 @@ __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, co
         if (lane == 0 && count)
             atomicAdd(&s_count, count);
         __syncthreads();
-        if (tid == 0)
+        if (tid == 0) {
             row_nnz[row] = s_count;
+            if (keep_slot)
+                keep_slot[row] = idx;
+        }
     }
 }
 
@@ -309,24 +318,43 @@ __global__ void __launch_bounds__(256) k_num_warp(MatView A, MatView B, const in
     }
 }
 
-// One CTA per row, nnz_i <= SLOTS/2; the whole table is bitonic-sorted by key in
-// shared memory (empty slots carry INT32_MAX and sink to the end).
-template <int SLOTS, int THREADS>
+// One CTA per row, nnz_i <= SLOTS/2.  After the hash accumulation the occupied slots are
+// DISTRIBUTION-sorted: the (distinct) keys are dealt into NBUCK buckets by a monotone
+// linear map of [kmin, kmax], a block scan turns bucket counts into offsets, the entries
+// are scattered straight into the output row, and every bucket (about one entry on
+// average) is finished by an insertion sort -- O(n) instead of a bitonic sort of the whole
+// table.  Badly clustered keys (a bucket of more than NUM_BUCKET_MAX entries) fall back to
+// the bitonic sort in shared memory.
+constexpr int NUM_BUCKET_MAX = 24;
+
+template <int SLOTS, int THREADS, int NBUCK>
 __global__ void __launch_bounds__(THREADS) k_num_cta(MatView A, MatView B, const int32_t *__restrict__ rows,
                                                      const int64_t *__restrict__ c_rp, int32_t *__restrict__ c_ci,
                                                      double *__restrict__ c_vs, int both_f32)
 {
+    static_assert(NBUCK % THREADS == 0, "one scan pass");
     extern __shared__ __align__(16) unsigned char s_raw[];
     double *vals = reinterpret_cast<double *>(s_raw);
     int32_t *keys = reinterpret_cast<int32_t *>(s_raw + sizeof(double) * SLOTS);
+    unsigned *cnt = reinterpret_cast<unsigned *>(s_raw + (sizeof(double) + sizeof(int32_t)) * SLOTS);
+    __shared__ int s_min, s_max, s_big;
+    __shared__ int s_wt[33];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int i = tid; i < SLOTS; i += THREADS) {
         keys[i] = EMPTY_KEY;
         vals[i] = 0.0;
     }
+    for (int i = tid; i < NBUCK; i += THREADS)
+        cnt[i] = 0;
+    if (tid == 0) {
+        s_min = INT32_MAX;
+        s_max = -1;
+        s_big = 0;
+    }
     __syncthreads();
     const int32_t row = rows[blockIdx.x];
     const int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+    int kmin = INT32_MAX, kmax = -1;
     for (int64_t jj = as + w; jj < ae; jj += THREADS / 32) {
         const int32_t j = A.ci[jj];
         const double av = ld_val(A.vs, A.vk, jj);
@@ -334,6 +362,8 @@ __global__ void __launch_bounds__(THREADS) k_num_cta(MatView A, MatView B, const
         for (int64_t kk = bs + lane; kk < be; kk += 32) {
             const int32_t k = B.ci[kk];
             const double p = product(av, ld_val(B.vs, B.vk, kk), both_f32);
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
             unsigned h = hash_col(k, SLOTS - 1);
             while (true) {
                 const int32_t old = atomicCAS(&keys[h], EMPTY_KEY, k);
@@ -345,8 +375,78 @@ __global__ void __launch_bounds__(THREADS) k_num_cta(MatView A, MatView B, const
             }
         }
     }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0 && kmax >= 0) {
+        atomicMin(&s_min, kmin);
+        atomicMax(&s_max, kmax);
+    }
     __syncthreads();
-    // bitonic sort of (key, val) over all SLOTS
+    const int64_t out = c_rp[row];
+    const int nz = (int)(c_rp[row + 1] - out);
+    kmin = s_min;
+    const uint64_t range = (uint64_t)(s_max - kmin) + 1;
+    const uint64_t scale = ((uint64_t)NBUCK << 32) / range;  // bucket = (k - kmin) * NBUCK / range, monotone in k
+    // bucket counts
+    for (int i = tid; i < SLOTS; i += THREADS) {
+        const int32_t k = keys[i];
+        if (k != EMPTY_KEY)
+            atomicAdd(&cnt[(unsigned)(((uint64_t)(k - kmin) * scale) >> 32)], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the counts (NBUCK/THREADS consecutive buckets per thread)
+    {
+        constexpr int PER = NBUCK / THREADS;
+        unsigned loc[PER];
+        int sum = 0, big = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            loc[q] = cnt[tid * PER + q];
+            sum += loc[q];
+            big |= loc[q] > NUM_BUCKET_MAX;
+        }
+        if (big)
+            s_big = 1;
+        int tot;
+        int ex = block_exclusive_scan<int>(sum, s_wt, tot);
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            cnt[tid * PER + q] = ex;
+            ex += loc[q];
+        }
+    }
+    __syncthreads();
+    if (!s_big) {
+        // scatter into the output row; cnt[b] becomes the END of bucket b
+        for (int i = tid; i < SLOTS; i += THREADS) {
+            const int32_t k = keys[i];
+            if (k != EMPTY_KEY) {
+                const unsigned b = (unsigned)(((uint64_t)(k - kmin) * scale) >> 32);
+                const unsigned pos = atomicAdd(&cnt[b], 1u);
+                c_ci[out + pos] = k;
+                c_vs[out + pos] = vals[i];
+            }
+        }
+        __syncthreads();
+        // finish every bucket with an insertion sort (columns are distinct)
+        for (int b = tid; b < NBUCK; b += THREADS) {
+            const int s0 = b ? (int)cnt[b - 1] : 0, e0 = (int)cnt[b];
+            for (int i = s0 + 1; i < e0; i++) {
+                const int32_t k = c_ci[out + i];
+                const double v = c_vs[out + i];
+                int j = i - 1;
+                while (j >= s0 && c_ci[out + j] > k) {
+                    c_ci[out + j + 1] = c_ci[out + j];
+                    c_vs[out + j + 1] = c_vs[out + j];
+                    j--;
+                }
+                c_ci[out + j + 1] = k;
+                c_vs[out + j + 1] = v;
+            }
+        }
+        return;
+    }
+    // fallback: bitonic sort of (key, val) over all SLOTS
     for (int k = 2; k <= SLOTS; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < SLOTS / 2; t += THREADS) {
@@ -365,8 +465,6 @@ __global__ void __launch_bounds__(THREADS) k_num_cta(MatView A, MatView B, const
             __syncthreads();
         }
     }
-    const int64_t out = c_rp[row];
-    const int nz = (int)(c_rp[row + 1] - out);
     for (int i = tid; i < nz; i += THREADS) {
         c_ci[out + i] = keys[i];
         c_vs[out + i] = vals[i];
@@ -374,28 +472,36 @@ __global__ void __launch_bounds__(THREADS) k_num_cta(MatView A, MatView B, const
 }
 
 // ---------------------------------------------------- numeric: dense (heavy rows)
-// Dense float64 accumulator of B.ncols entries + bitmap per persistent CTA
-// (shared memory when SMEM_ACC, else this CTA's slice of zeroed global scratch,
-// which on B200 stays L2-resident).  The sweep walks the bitmap in column order,
-// so the row comes out sorted; accumulator and bitmap are zeroed as they are read.
+// Dense float64 accumulator + column bitmap per persistent CTA; the sweep walks the
+// bitmap in column order, so the row comes out sorted, and zeroes what it reads.
+//   SMEM_ACC   the accumulator covers a WINDOW of `win` columns in shared memory and the
+//              row is done in ceil(ncols/win) passes over its products (one pass when the
+//              whole row fits); shared-memory float64 CAS adds were measured ~2x faster
+//              than L2 RED.F64 here.
+//   otherwise  accumulator and bitmap are this CTA's slice of zeroed global scratch (stays
+//              L2-resident on B200); used when ncols would need too many passes.
+// If the symbolic phase kept the row's bitmap (`keep`), the numeric phase issues ONE atomic
+// per product (the add) instead of two (add + bitmap OR).
 template <bool SMEM_ACC, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_num_dense(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin,
                                                        const int64_t *__restrict__ c_rp, int32_t *__restrict__ c_ci,
                                                        double *__restrict__ c_vs, int both_f32, double *__restrict__ gacc,
-                                                       unsigned *__restrict__ gbm, int n_cols, int n_words,
-                                                       int *__restrict__ work_counter)
+                                                       unsigned *__restrict__ gbm, int n_cols, int win,
+                                                       int *__restrict__ work_counter, const unsigned *__restrict__ keep,
+                                                       const int32_t *__restrict__ keep_slot)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_idx;
     __shared__ int s_wt[33];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int win_words = (win + 31) >> 5, n_words = (n_cols + 31) >> 5;
     double *acc = SMEM_ACC ? reinterpret_cast<double *>(s_raw) : gacc + (size_t)blockIdx.x * n_cols;
-    unsigned *bm = SMEM_ACC ? reinterpret_cast<unsigned *>(s_raw + sizeof(double) * (size_t)n_cols)
+    unsigned *bm = SMEM_ACC ? reinterpret_cast<unsigned *>(s_raw + sizeof(double) * (size_t)win)
                             : gbm + (size_t)blockIdx.x * n_words;
     if (SMEM_ACC) {
-        for (int i = tid; i < n_cols; i += THREADS)
+        for (int i = tid; i < win; i += THREADS)
             acc[i] = 0.0;
-        for (int i = tid; i < n_words; i += THREADS)
+        for (int i = tid; i < win_words; i += THREADS)
             bm[i] = 0;
     }
     while (true) {
@@ -408,48 +514,269 @@ __global__ void __launch_bounds__(THREADS) k_num_dense(MatView A, MatView B, con
             break;
         const int32_t row = rows[idx];
         const int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
-        for (int64_t jj = as + w; jj < ae; jj += THREADS / 32) {
-            const int32_t j = A.ci[jj];
-            const double av = ld_val(A.vs, A.vk, jj);
-            const int64_t bs = ld_rp(B.rp, B.rp64, j), be = ld_rp(B.rp, B.rp64, (int64_t)j + 1);
-            for (int64_t kk = bs + lane; kk < be; kk += 32) {
-                const int32_t k = B.ci[kk];
-                const double p = product(av, ld_val(B.vs, B.vk, kk), both_f32);
-                atomicOr(&bm[k >> 5], 1u << (k & 31));
-                atomicAdd(&acc[k], p);
-            }
-        }
-        __syncthreads();
+        const unsigned *kept = keep ? keep + (size_t)keep_slot[row] * n_words : nullptr;
         int64_t out = c_rp[row];
-        for (int base = 0; base < n_words; base += THREADS) {
-            const int i = base + tid;
-            unsigned bits = 0;
-            if (i < n_words)
-                bits = SMEM_ACC ? bm[i] : __ldcg(&bm[i]);
-            int tot;
-            int off = block_exclusive_scan<int>(__popc(bits), s_wt, tot);
-            if (bits) {
-                if (SMEM_ACC)
-                    bm[i] = 0;
-                else
-                    __stcg(&bm[i], 0u);
+        for (int c0 = 0; c0 < n_cols; c0 += win) {  // win is a multiple of 32; one pass when !SMEM_ACC
+            const int c1 = min(c0 + win, n_cols);
+            for (int64_t jj = as + w; jj < ae; jj += THREADS / 32) {
+                const int32_t j = A.ci[jj];
+                const double av = ld_val(A.vs, A.vk, jj);
+                const int64_t bs = ld_rp(B.rp, B.rp64, j), be = ld_rp(B.rp, B.rp64, (int64_t)j + 1);
+                for (int64_t kk = bs + lane; kk < be; kk += 32) {
+                    const int32_t k = B.ci[kk];
+                    if (k >= c0 && k < c1) {
+                        const double p = product(av, ld_val(B.vs, B.vk, kk), both_f32);
+                        const int kl = k - c0;
+                        if (!kept)
+                            atomicOr(&bm[kl >> 5], 1u << (kl & 31));
+                        atomicAdd(&acc[kl], p);
+                    }
+                }
+            }
+            __syncthreads();
+            const int nw = (c1 - c0 + 31) >> 5;
+            for (int base = 0; base < nw; base += THREADS) {
+                const int i = base + tid;
+                unsigned bits = 0;
+                if (i < nw)
+                    bits = kept ? kept[(c0 >> 5) + i] : (SMEM_ACC ? bm[i] : __ldcg(&bm[i]));
+                int tot;
+                const int off = block_exclusive_scan<int>(__popc(bits), s_wt, tot);
+                if (bits) {
+                    if (!kept) {
+                        if (SMEM_ACC)
+                            bm[i] = 0;
+                        else
+                            __stcg(&bm[i], 0u);
+                    }
+                    int64_t o = out + off;
+                    while (bits) {
+                        const int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const int kl = i * 32 + b;
+                        c_ci[o] = c0 + kl;
+                        if (SMEM_ACC) {
+                            c_vs[o] = acc[kl];
+                            acc[kl] = 0.0;
+                        } else {
+                            c_vs[o] = __ldcg(&acc[kl]);
+                            __stcg(&acc[kl], 0.0);
+                        }
+                        o++;
+                    }
+                }
+                out += tot;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------- numeric: dense, owner-computes (no atomics)
+// For heavy rows when B's rows are strictly increasing in column (always true for the
+// transposed operand of A*B^T) and the symbolic bitmaps were kept.  The accumulator window
+// is cut into OWN_NW column ranges of about equal B-entry mass, one per warp, and every B row
+// is pre-split at those boundaries (k_own_split), so warp w only ever touches its own range:
+// plain LDS / DMUL / DADD / STS, no atomics, and every output element is summed in A-row
+// order -- the reference's own order (multiply.py:111-120), so values are bit-identical.
+// Lanes fetch the metadata of 32 A entries at once; the B pieces of OWN_DEPTH entries are in
+// flight before the first is consumed.
+constexpr int OWN_NW = 16, OWN_DEPTH = 16;
+
+__global__ void k_col_hist(const int32_t *__restrict__ ci, int64_t nnz, int *__restrict__ cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz)
+        atomicAdd(&cnt[ci[i]], 1);
+}
+
+// is some row of B not strictly increasing in column?
+__global__ void k_rows_not_strict(MatView B, int *__restrict__ flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i >= B.nnz)
+        return;
+    if (B.ci[i - 1] >= B.ci[i]) {
+        // is i a row start?
+        int64_t lo = 0, hi = (int64_t)B.nrows + 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (ld_rp(B.rp, B.rp64, mid) < i)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (!(lo <= B.nrows && ld_rp(B.rp, B.rp64, lo) == i))
+            *flag = 1;
+    }
+}
+
+// bounds[q*nwarps + w]: first column of warp w's range in window q (mass-balanced inside the window)
+__global__ void k_own_bounds(const int64_t *__restrict__ cum, int n, int win, int passes, int nwarps,
+                             int32_t *__restrict__ bounds)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > passes * nwarps)
+        return;
+    if (i == passes * nwarps) {
+        bounds[i] = n;
+        return;
+    }
+    const int q = i / nwarps, w = i % nwarps;
+    const int c0 = q * win, c1 = min(c0 + win, n);
+    if (w == 0) {
+        bounds[i] = c0;
+        return;
+    }
+    const int64_t target = cum[c0] + (cum[c1] - cum[c0]) * w / nwarps;
+    bounds[i] = (int32_t)lower_bound_rp(cum, (int64_t)c0, (int64_t)c1, target);
+}
+
+// split[j*(nb+1) + k]: offset inside B row j of its first entry with column >= bounds[k]
+__global__ void k_own_split(MatView B, const int32_t *__restrict__ bounds, int nb, int32_t *__restrict__ split)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B.nrows * (nb + 1))
+        return;
+    const int64_t j = i / (nb + 1);
+    const int k = (int)(i % (nb + 1));
+    const int64_t bs = ld_rp(B.rp, B.rp64, j), be = ld_rp(B.rp, B.rp64, j + 1);
+    const int32_t key = bounds[k];
+    int64_t lo = bs, hi = be;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (B.ci[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    split[i] = (int32_t)(lo - bs);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_num_owner(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, const int64_t *__restrict__ c_rp,
+            int32_t *__restrict__ c_ci, double *__restrict__ c_vs, int both_f32, int n_cols, int win, int passes,
+            int *__restrict__ work_counter, const unsigned *__restrict__ keep, const int32_t *__restrict__ keep_slot,
+            const int32_t *__restrict__ split)
+{
+    constexpr int THREADS = NW * 32;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int s_idx;
+    __shared__ int s_wt[33];
+    double *acc = reinterpret_cast<double *>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n_words = (n_cols + 31) >> 5, nb = passes * NW;
+    for (int i = tid; i < win; i += THREADS)
+        acc[i] = 0.0;
+    while (true) {
+        __syncthreads();
+        if (tid == 0)
+            s_idx = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int idx = s_idx;
+        if (idx >= nbin)
+            break;
+        const int32_t row = rows[idx];
+        const int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+        const unsigned *kept = keep + (size_t)keep_slot[row] * n_words;
+        int64_t out = c_rp[row];
+        for (int q = 0; q < passes; q++) {
+            const int c0 = q * win, c1 = min(c0 + win, n_cols);
+            const int kidx = q * NW + w;
+            // metadata of the next 32 A entries is fetched while the current 32 are consumed
+            int32_t jn = 0;
+            double avn = 0.0;
+            if (as + lane < ae) {
+                jn = A.ci[as + lane];
+                avn = ld_val(A.vs, A.vk, as + lane);
+            }
+            for (int64_t base = as; base < ae; base += 32) {
+                const bool valid = base + lane < ae;
+                const int32_t j = jn;
+                const double av = avn;
+                if (base + 32 + lane < ae) {
+                    jn = A.ci[base + 32 + lane];
+                    avn = ld_val(A.vs, A.vk, base + 32 + lane);
+                }
+                int64_t start = 0;
+                int len = 0;
+                if (valid) {
+                    const int32_t *sp = split + (size_t)j * (nb + 1) + kidx;
+                    const int s_off = sp[0];
+                    len = sp[1] - s_off;
+                    start = ld_rp(B.rp, B.rp64, j) + s_off;
+                }
+                // The work of these 32 pieces is cut into UNITS of <= 32 consecutive B entries,
+                // enumerated in piece order (an inclusive warp scan of the unit counts locates the
+                // piece of unit i), so long pieces pipeline like short ones and every accumulator
+                // still sees its contributions in A-row order.
+                const int cu = (len + 31) >> 5;
+                int incl = cu;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o)
+                        incl += t;
+                }
+                const int excl = incl - cu;
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                for (int i0 = 0; i0 < total; i0 += OWN_DEPTH) {
+                    int col[OWN_DEPTH];
+                    double val[OWN_DEPTH];
+                    int meta[OWN_DEPTH];  // (piece lane << 8) | entries in the unit
+#pragma unroll
+                    for (int d = 0; d < OWN_DEPTH; d++) {
+                        const int i = i0 + d;
+                        col[d] = c0;
+                        val[d] = 0.0;
+                        meta[d] = 0;
+                        if (i < total) {
+                            const int u = __popc(__ballot_sync(0xffffffffu, excl <= i)) - 1;
+                            const int off = (i - __shfl_sync(0xffffffffu, excl, u)) << 5;
+                            const int64_t st = __shfl_sync(0xffffffffu, start, u) + off;
+                            const int ln = min(32, __shfl_sync(0xffffffffu, len, u) - off);
+                            meta[d] = (u << 8) | ln;
+                            if (lane < ln) {
+                                col[d] = B.ci[st + lane];
+                                val[d] = ld_val(B.vs, B.vk, st + lane);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < OWN_DEPTH; d++) {
+                        if (i0 + d < total) {
+                            const double avu = __shfl_sync(0xffffffffu, av, meta[d] >> 8);
+                            if (lane < (meta[d] & 255)) {
+                                const int kl = col[d] - c0;
+                                acc[kl] = __dadd_rn(acc[kl], product(avu, val[d], both_f32));
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // sweep the window in column order with the bitmap kept by the symbolic phase
+            const int nw = (c1 - c0 + 31) >> 5;
+            for (int wb = 0; wb < nw; wb += THREADS) {
+                const int i = wb + tid;
+                unsigned bits = i < nw ? kept[(c0 >> 5) + i] : 0u;
+                int tot;
+                const int off = block_exclusive_scan<int>(__popc(bits), s_wt, tot);
                 int64_t o = out + off;
                 while (bits) {
                     const int b = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    const int k = i * 32 + b;
-                    c_ci[o] = k;
-                    if (SMEM_ACC) {
-                        c_vs[o] = acc[k];
-                        acc[k] = 0.0;
-                    } else {
-                        c_vs[o] = __ldcg(&acc[k]);
-                        __stcg(&acc[k], 0.0);
-                    }
+                    const int kl = i * 32 + b;
+                    c_ci[o] = c0 + kl;
+                    c_vs[o] = acc[kl];
+                    acc[kl] = 0.0;
                     o++;
                 }
+                out += tot;
             }
-            out += tot;
+            __syncthreads();
         }
     }
 }
@@ -487,10 +814,16 @@ template <typename K> static int optin_smem(K kernel, size_t bytes)
     return CSRK_OK;
 }
 
-// symbolic thresholds on P_i (products) and numeric thresholds on nnz_i
-constexpr int SYM_WARP_SLOTS = 256, SYM_CTA1_SLOTS = 4096, SYM_CTA2_SLOTS = 32768;
-constexpr int NUM_WARP_SLOTS = 128, NUM_CTA1_SLOTS = 2048, NUM_CTA2_SLOTS = 16384;
+// symbolic bins on P_i (products): hash sets of 2x the bound, then the bitmap;
+// numeric bins on nnz_i: hash accumulators of 2x the bound, then the dense accumulator.
+// The bitmap/dense boundaries coincide (8192) so that every dense-numeric row went
+// through the symbolic bitmap kernel and can reuse its stored bitmap.
+constexpr int SYM_WARP_SLOTS = 256, SYM_C1 = 2048, SYM_C2 = 8192, SYM_C3 = 16384;
+constexpr int NUM_WARP_SLOTS = 128, NUM_C1 = 1024, NUM_C2 = 4096, NUM_C3 = 16384;
 constexpr int DENSE_THREADS = 512;
+constexpr int DENSE_WIN = 28160;                      // max columns per shared-memory accumulator window (220 KB)
+constexpr int DENSE_MAX_PASSES = 4;                   // beyond that: global scratch, one pass
+constexpr size_t KEEP_BITMAP_BUDGET = (size_t)8 << 30;  // bytes of symbolic bitmaps kept for the numeric phase
 
 static int make_empty_result(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
 {
@@ -529,7 +862,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                 total.as<unsigned long long>());
 
     // ---- step 1: symbolic
-    BinSpec sspec{{0, SYM_WARP_SLOTS / 2, SYM_CTA1_SLOTS / 2, SYM_CTA2_SLOTS / 2, INT64_MAX}};
+    BinSpec sspec{{0, SYM_WARP_SLOTS / 2, SYM_C1 / 2, SYM_C2 / 2, SYM_C3 / 2, INT64_MAX}};
     int cnt[NBINS], off[NBINS + 1];
     DevBuf list;
     CSRK_TRY(bin_rows(prod.as<int64_t>(), (int64_t)m, sspec, cnt, off, list, s));
@@ -544,29 +877,37 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
         CSRK_LAUNCH((k_sym_warp<SYM_WARP_SLOTS>), (unsigned)div_up(cnt[1], 8), 256, 0, s, A, B, L + off[1], cnt[1],
                     row_nnz.as<int32_t>());
     if (cnt[2]) {
-        auto k = k_sym_cta<SYM_CTA1_SLOTS, 128>;
-        CSRK_LAUNCH(k, (unsigned)cnt[2], 128, SYM_CTA1_SLOTS * 4, s, A, B, L + off[2], row_nnz.as<int32_t>());
+        auto k = k_sym_cta<SYM_C1, 128>;
+        CSRK_LAUNCH(k, (unsigned)cnt[2], 128, SYM_C1 * 4, s, A, B, L + off[2], row_nnz.as<int32_t>());
     }
     if (cnt[3]) {
-        auto k = k_sym_cta<SYM_CTA2_SLOTS, 256>;
-        CSRK_TRY(optin_smem(k, SYM_CTA2_SLOTS * 4));
-        CSRK_LAUNCH(k, (unsigned)cnt[3], 256, SYM_CTA2_SLOTS * 4, s, A, B, L + off[3], row_nnz.as<int32_t>());
+        auto k = k_sym_cta<SYM_C2, 128>;
+        CSRK_LAUNCH(k, (unsigned)cnt[3], 128, SYM_C2 * 4, s, A, B, L + off[3], row_nnz.as<int32_t>());
     }
-    DevBuf gbm;
     if (cnt[4]) {
+        auto k = k_sym_cta<SYM_C3, 256>;
+        CSRK_TRY(optin_smem(k, SYM_C3 * 4));
+        CSRK_LAUNCH(k, (unsigned)cnt[4], 256, SYM_C3 * 4, s, A, B, L + off[4], row_nnz.as<int32_t>());
+    }
+    DevBuf gbm, keep, keep_slot;
+    if (cnt[5]) {
         const size_t bm_bytes = (size_t)n_words * 4;
+        if (bm_bytes * (size_t)cnt[5] <= KEEP_BITMAP_BUDGET) {
+            CSRK_TRY(keep.alloc(bm_bytes * (size_t)cnt[5], s));
+            CSRK_TRY(keep_slot.alloc(sizeof(int32_t) * (size_t)m, s));
+        }
         if (bm_bytes + 1024 <= smem_max - 8 * 1024) {
             auto k = k_sym_bitmap<true, DENSE_THREADS>;
             CSRK_TRY(optin_smem(k, bm_bytes));
-            const int grid = (int)std::min((int64_t)cnt[4], (int64_t)sms * (bm_bytes > 100 * 1024 ? 1 : 2));
-            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes, s, A, B, L + off[4], cnt[4], row_nnz.as<int32_t>(),
-                        (unsigned *)nullptr, n_words, counter.as<int>());
+            const int grid = (int)std::min((int64_t)cnt[5], (int64_t)sms * (bm_bytes > 100 * 1024 ? 1 : 2));
+            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
+                        (unsigned *)nullptr, n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>());
         } else {
             auto k = k_sym_bitmap<false, DENSE_THREADS>;
-            const int grid = (int)std::min((int64_t)cnt[4], (int64_t)sms * 2);
+            const int grid = (int)std::min((int64_t)cnt[5], (int64_t)sms * 2);
             CSRK_TRY(gbm.alloc_zero(bm_bytes * (size_t)grid, s));
-            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, L + off[4], cnt[4], row_nnz.as<int32_t>(),
-                        gbm.as<unsigned>(), n_words, counter.as<int>());
+            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
+                        gbm.as<unsigned>(), n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>());
         }
     }
 
@@ -577,7 +918,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     int64_t Z = 0;
     CSRK_CUDA(cudaMemcpyAsync(&Z, rp64.as<int64_t>() + m, sizeof Z, cudaMemcpyDeviceToHost, s));
     // numeric binning (its sync also lands Z and P)
-    BinSpec nspec{{0, NUM_WARP_SLOTS / 2, NUM_CTA1_SLOTS / 2, NUM_CTA2_SLOTS / 2, INT64_MAX}};
+    BinSpec nspec{{0, NUM_WARP_SLOTS / 2, NUM_C1 / 2, NUM_C2 / 2, NUM_C3 / 2, INT64_MAX}};
     int ncnt[NBINS], noff[NBINS + 1];
     DevBuf nlist;
     CSRK_TRY(bin_rows(row_nnz.as<int32_t>(), (int64_t)m, nspec, ncnt, noff, nlist, s));
@@ -609,31 +950,83 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
             CSRK_LAUNCH((k_num_warp<NUM_WARP_SLOTS>), (unsigned)div_up(ncnt[1], 8), 256, 0, s, A, B, NL + noff[1], ncnt[1],
                         crp, out->ci, cvs, both_f32);
         if (ncnt[2]) {
-            auto k = k_num_cta<NUM_CTA1_SLOTS, 128>;
-            CSRK_LAUNCH(k, (unsigned)ncnt[2], 128, NUM_CTA1_SLOTS * 12, s, A, B, NL + noff[2], crp, out->ci, cvs, both_f32);
+            auto k = k_num_cta<NUM_C1, 128, 512>;
+            CSRK_LAUNCH(k, (unsigned)ncnt[2], 128, NUM_C1 * 12 + 512 * 4, s, A, B, NL + noff[2], crp, out->ci, cvs, both_f32);
         }
         if (ncnt[3]) {
-            auto k = k_num_cta<NUM_CTA2_SLOTS, 512>;
-            CSRK_TRY(optin_smem(k, NUM_CTA2_SLOTS * 12));
-            CSRK_LAUNCH(k, (unsigned)ncnt[3], 512, NUM_CTA2_SLOTS * 12, s, A, B, NL + noff[3], crp, out->ci, cvs, both_f32);
+            auto k = k_num_cta<NUM_C2, 256, 2048>;
+            CSRK_TRY(optin_smem(k, NUM_C2 * 12 + 2048 * 4));
+            CSRK_LAUNCH(k, (unsigned)ncnt[3], 256, NUM_C2 * 12 + 2048 * 4, s, A, B, NL + noff[3], crp, out->ci, cvs,
+                        both_f32);
         }
         if (ncnt[4]) {
-            const size_t acc_bytes = (size_t)n * 8 + (size_t)n_words * 4;
+            auto k = k_num_cta<NUM_C3, 512, 4096>;
+            CSRK_TRY(optin_smem(k, NUM_C3 * 12 + 4096 * 4));
+            CSRK_LAUNCH(k, (unsigned)ncnt[4], 512, NUM_C3 * 12 + 4096 * 4, s, A, B, NL + noff[4], crp, out->ci, cvs,
+                        both_f32);
+        }
+        if (ncnt[5]) {
             int *wc = counter.as<int>() + 1;
-            if (acc_bytes + 1024 <= smem_max - 8 * 1024) {
+            const unsigned *kp = keep.as<unsigned>();
+            const int32_t *ks = keep_slot.as<int32_t>();
+            const int passes = (int)div_up((int64_t)n, DENSE_WIN);
+            bool owner = passes <= DENSE_MAX_PASSES && kp != nullptr && n >= 1024;
+            if (owner) {
+                // owner-computes needs B's rows strictly increasing in column
+                DevBuf flag;
+                CSRK_TRY(flag.alloc_zero(sizeof(int), s));
+                if (b->nnz > 1)
+                    CSRK_LAUNCH(k_rows_not_strict, (unsigned)div_up(b->nnz - 1, 256), 256, 0, s, B, flag.as<int>());
+                int bad = 0;
+                CSRK_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+                CSRK_CUDA(cudaStreamSynchronize(s));
+                owner = !bad;
+            }
+            if (owner) {
+                const int win = (int)(div_up(div_up((int64_t)n, passes), 32) * 32);
+                const int own_nw = options().own_nw.load() == 8 ? 8 : 16;
+                const int nb = passes * own_nw;
+                DevBuf hist, cum, bounds, split;
+                CSRK_TRY(hist.alloc_zero(sizeof(int) * ((size_t)n + 1), s));
+                CSRK_TRY(cum.alloc(sizeof(int64_t) * ((size_t)n + 1), s));
+                CSRK_TRY(bounds.alloc(sizeof(int32_t) * ((size_t)nb + 1), s));
+                CSRK_TRY(split.alloc(sizeof(int32_t) * (size_t)b->nrows * (nb + 1), s));
+                CSRK_LAUNCH(k_col_hist, (unsigned)div_up(b->nnz, 256), 256, 0, s, b->ci, b->nnz, hist.as<int>());
+                CSRK_TRY((exclusive_scan<int64_t>(ArrayLoader<int>{hist.as<int>()}, (int64_t)n, cum.as<int64_t>(), s)));
+                CSRK_LAUNCH(k_own_bounds, (unsigned)div_up(nb + 1, 64), 64, 0, s, cum.as<int64_t>(), (int)n, win, passes, own_nw,
+                            bounds.as<int32_t>());
+                CSRK_LAUNCH(k_own_split, (unsigned)div_up((int64_t)b->nrows * (nb + 1), 256), 256, 0, s, B,
+                            bounds.as<int32_t>(), nb, split.as<int32_t>());
+                const size_t bytes = (size_t)win * 8;
+                const int grid = (int)std::min((int64_t)ncnt[5], (int64_t)sms);
+                if (own_nw == 8) {
+                    auto k = k_num_owner<8>;
+                    CSRK_TRY(optin_smem(k, bytes));
+                    CSRK_LAUNCH(k, (unsigned)grid, 8 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>());
+                } else {
+                    auto k = k_num_owner<16>;
+                    CSRK_TRY(optin_smem(k, bytes));
+                    CSRK_LAUNCH(k, (unsigned)grid, 16 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>());
+                }
+            } else if (passes <= DENSE_MAX_PASSES) {
+                const int win = (int)(div_up(div_up((int64_t)n, passes), 32) * 32);  // balanced windows
+                const size_t bytes = (size_t)win * 8 + (size_t)(win / 32 + 1) * 4;
                 auto k = k_num_dense<true, DENSE_THREADS>;
-                CSRK_TRY(optin_smem(k, acc_bytes));
-                const int grid = (int)std::min((int64_t)ncnt[4], (int64_t)sms * (acc_bytes > 100 * 1024 ? 1 : 2));
-                CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, acc_bytes, s, A, B, NL + noff[4], ncnt[4], crp, out->ci, cvs,
-                            both_f32, (double *)nullptr, (unsigned *)nullptr, (int)n, n_words, wc);
+                CSRK_TRY(optin_smem(k, bytes));
+                const int grid = (int)std::min((int64_t)ncnt[5], (int64_t)sms * (bytes > 100 * 1024 ? 1 : 2));
+                CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs,
+                            both_f32, (double *)nullptr, (unsigned *)nullptr, (int)n, win, wc, kp, ks);
             } else {
                 auto k = k_num_dense<false, DENSE_THREADS>;
-                const int grid = (int)std::min((int64_t)ncnt[4], (int64_t)sms * 2);
+                const int grid = (int)std::min((int64_t)ncnt[5], (int64_t)sms * 2);
                 DevBuf gacc, gbm2;
                 CSRK_TRY(gacc.alloc_zero((size_t)n * 8 * (size_t)grid, s));
                 CSRK_TRY(gbm2.alloc_zero((size_t)n_words * 4 * (size_t)grid, s));
-                CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, NL + noff[4], ncnt[4], crp, out->ci, cvs, both_f32,
-                            gacc.as<double>(), gbm2.as<unsigned>(), (int)n, n_words, wc);
+                const int win = n_words * 32;  // one pass over all columns
+                CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                            gacc.as<double>(), gbm2.as<unsigned>(), (int)n, win, wc, kp, ks);
             }
         }
         return CSRK_OK;

@@ -162,6 +162,28 @@ def test_item_item_abt(kernel, dtype):
     _check_mm(kernel, M, M, True, 1e-10)
 
 
+def test_item_item_owner_path_is_bit_exact(kernel):
+    """Rows with > 8192 output entries and a sorted (transposed) right operand take the
+    owner-computes dense kernel: no atomics, and every output element is summed in the
+    reference's own order, so the VALUES are bit-identical to the oracle too."""
+    R = synth.powerlaw_csr(16000, 12000, 1_600_000, seed=81, dtype="f8", alpha=0.5, cap=600, min_len=20, col_skew=2.0)
+    M = R.transpose()
+    ref = orc.mult_abt(M, M)
+    rp, ci, vs = canonical(ref)
+    assert np.diff(rp).max() > 8192
+    mh = kernel.to_handle(M)
+    try:
+        ch = kernel.mult_abt(mh, mh)
+        got = kernel.from_handle(ch)
+        kernel.release_handle(ch)
+    finally:
+        kernel.release_handle(mh)
+    assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
+    heavy = np.repeat(np.diff(rp) > 8192, np.diff(rp))
+    assert np.array_equal(got.values[heavy], vs[heavy]), "owner path must reproduce the reference bit for bit"
+    assert_values_close(got.values, vs, 1e-10, float(np.abs(vs).max()))
+
+
 def test_virtual_ranks_row_blocks(kernel):
     """N ranks emulated as N row shards on one GPU; the concatenation equals
     the unsharded result (structure exactly; values up to atomic ordering)."""
