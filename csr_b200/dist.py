@@ -40,6 +40,12 @@ def partition_rows(rowptrs, nparts: int):
     return cuts
 
 
+def partition_by_weight(weights, nparts: int):
+    """Row boundaries giving blocks of ~equal total weight (e.g. the SpGEMM products per row)."""
+    cum = np.concatenate([[0], np.cumsum(np.asarray(weights, dtype=np.int64))])
+    return partition_rows(cum, nparts)
+
+
 def _dist():
     import torch.distributed as dist
     return dist
