@@ -19,6 +19,7 @@ is duck-typed and accepts the reference's own ``csr.CSR`` objects as well.
 from __future__ import annotations
 
 import logging
+import weakref
 
 import numpy as np
 
@@ -28,13 +29,57 @@ INTC = np.iinfo(np.intc)
 _log = logging.getLogger(__name__)
 
 
+class _HandleCache:
+    """
+    Device residency at the CSR-object level.
+
+    The reference's ``CSR.mult_vec`` makes a kernel handle on every call
+    (csr/csr.py:582), which is free for the numba kernel but is a full H2D upload here.
+    With ``CSR.keep_resident(True)`` a matrix keeps ONE handle per kernel alive for as
+    long as its three arrays are the same objects; the handle is released when the
+    matrix is garbage-collected, when its values are re-assigned, or on
+    ``CSR.keep_resident(False)``.  In-place writes into the arrays are NOT tracked
+    ("modifying the matrix is not guaranteed to modify handles created from it",
+    csr/kernels/numba/__init__.py:24-26), so this is opt-in.
+    """
+
+    def __init__(self):
+        self.entries = {}   # id(csr) -> (kernel, handle, (id(rowptrs), id(colinds), id(values)))
+
+    def get(self, csr, K):
+        key = id(csr)
+        sig = (id(csr.rowptrs), id(csr.colinds), id(csr._values), csr.nnz)
+        ent = self.entries.get(key)
+        if ent is not None and ent[0] is K and ent[2] == sig and getattr(ent[1], 'H', 1):
+            return ent[1]
+        self.drop(csr)
+        h = K.to_handle(csr)
+        self.entries[key] = (K, h, sig)
+        weakref.finalize(csr, self._finalize, key)
+        return h
+
+    def drop(self, csr):
+        self._finalize(id(csr))
+
+    def _finalize(self, key):
+        ent = self.entries.pop(key, None)
+        if ent is not None:
+            try:
+                ent[0].release_handle(ent[1])
+            except Exception:  # interpreter shutdown
+                pass
+
+
+_cache = _HandleCache()
+
+
 class CSR:
     """
     Compressed sparse row matrix: ``nrows, ncols, nnz, rowptrs, colinds, values``
     (values optional).  Same constructor and attribute contract as the reference.
     """
 
-    __slots__ = ("nrows", "ncols", "nnz", "rowptrs", "colinds", "_values")
+    __slots__ = ("nrows", "ncols", "nnz", "rowptrs", "colinds", "_values", "_resident", "__weakref__")
 
     def __init__(self, nrows, ncols, nnz, rps, cis, vs, _cast=True):
         # csr.py:79-100
@@ -57,6 +102,15 @@ class CSR:
         self.rowptrs = rps
         self.colinds = cis
         self._values = vs
+        self._resident = False
+
+    def keep_resident(self, flag=True):
+        """Keep this matrix's kernel handle alive between ``mult_vec`` / ``multiply`` calls
+        (see :class:`_HandleCache`).  Returns ``self``."""
+        self._resident = bool(flag)
+        if not flag:
+            _cache.drop(self)
+        return self
 
     # ------------------------------------------------------------ constructors
     @classmethod
@@ -144,6 +198,7 @@ class CSR:
                 vs = vs[:self.nnz]
             vs = np.require(vs, requirements='C')
         self._values = vs
+        _cache.drop(self)   # a cached handle holds the old values
 
     def _required_values(self):
         vs = self.values
@@ -244,6 +299,7 @@ class CSR:
         self.colinds[:] = s.colinds
         if self._values is not None:
             self._values[:] = s.values
+        _cache.drop(self)
 
     def _filter_zeros(self):
         """csr/_struct.py:61-79: drop stored zeros in place (host container utility;
@@ -259,6 +315,7 @@ class CSR:
         self.colinds = self.colinds[keep]
         self._values = self._values[keep]
         self.nnz = int(pos[-1])
+        _cache.drop(self)
 
     # ----------------------------------------------------------------- kernels
     def multiply(self, other, transpose=False):
@@ -304,6 +361,8 @@ class CSR:
         assert v.shape == (self.ncols,)
         K = get_kernel()
         if self.nnz <= K.max_nnz:
+            if self._resident:
+                return K.mult_vec(_cache.get(self, K), v)
             with releasing(K.to_handle(self), K) as h:
                 return K.mult_vec(h, v)
         else:

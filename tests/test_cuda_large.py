@@ -229,6 +229,28 @@ def test_structure_only_product(kernel):
     assert np.array_equal(got.values, ref[2])     # small integer counts: exact
 
 
+def test_keep_resident_handle_cache(kernel):
+    "CSR-level device residency: one upload for many mult_vec calls; dropped on new values / GC."
+    from csr_b200 import csr as csr_mod
+    A = synth.powerlaw_csr(500, 400, 6000, seed=91, dtype="f8").keep_resident()
+    x = synth.dense_vector(400, 92, "f8")
+    y1 = A.mult_vec(x)
+    h1 = csr_mod._cache.entries[id(A)][1]
+    y2 = A.mult_vec(x)
+    assert csr_mod._cache.entries[id(A)][1] is h1 and h1.H
+    assert np.array_equal(y1, y2)
+    assert_values_close(y1, orc.mult_vec(A, x), 1e-10, _mv_scale(A, x))
+    A.values = A.values * 2.0            # re-assigned values invalidate the cached handle
+    assert not h1.H and id(A) not in csr_mod._cache.entries
+    assert_values_close(A.mult_vec(x), 2.0 * y1, 1e-12, _mv_scale(A, x))
+    h2 = csr_mod._cache.entries[id(A)][1]
+    key = id(A)
+    del A
+    import gc
+    gc.collect()
+    assert key not in csr_mod._cache.entries and not h2.H
+
+
 def test_released_handle_is_rejected(kernel):
     h = kernel.to_handle(CSR.empty(3, 3))
     kernel.release_handle(h)
