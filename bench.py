@@ -37,6 +37,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 PER_GPU_ROWS = 1_000_000
 PER_GPU_NNZ = 100_000_000
@@ -171,7 +174,7 @@ def run_ours(args):
     x_host = np.random.default_rng(77).standard_normal(A.ncols).astype(np.float32)
     row_counts = [A.nrows] * world
     t0 = time.perf_counter()
-    ds = DistSpMV(A, row_counts, x_dtype="f4", kernel=K)
+    ds = DistSpMV(A, row_counts, x_dtype="f4", kernel=K, fused=args.fused)
     t_handle = time.perf_counter() - t0
     ds.set_x(x_host)
     log(f"[rank {rank}] block {A}  gen {t_gen:.1f}s  to_handle {t_handle:.2f}s")
@@ -258,7 +261,9 @@ def run_ours(args):
             "global_shape": [A.nrows * world, A.ncols], "global_nnz": A.nnz * world,
             "row_lengths": "rank-size power law alpha=1.0, mean 100, cap ncols, random row order",
             "columns": "stratified uniform" if args.col_skew == 1.0 else f"stratified, skew t^{args.col_skew}",
-            "parallelism": f"row-partitioned x{world}; step = NCCL broadcast(x) + local SpMV + all-gather(y)",
+            "parallelism": f"row-partitioned x{world}; step = NCCL broadcast(x) + " + (
+                "SpMV kernel storing y rows into every rank's buffer over NVLink (fused gather) + barrier"
+                if ds.symm is not None else "local SpMV + NCCL all-gather(y)"),
             "l2_policy": "inputs (>=0.8 GB per GPU) larger than the 126 MB L2; no flush needed",
             "bytes_per_step": int(total_bytes), "scale": args.scale,
         },
@@ -462,6 +467,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only)")
     ap.add_argument("--col-skew", type=float, default=1.0)
     ap.add_argument("--spgemm-scale", type=float, default=1.0, help="scale of configs[2] for the A*A^T leg (0 = skip)")
+    ap.add_argument("--fused", action="store_true", help="fused SpMV+gather over peer memory instead of the NCCL all-gather")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the SpMV kernel, if known")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "csrk_subset_rows": (_int, [_vp, _i32, _i32, _P(_vp)]),
     "csrk_spmv": (_int, [_vp, _vp, _int, _vp]),
     "csrk_spmv_dev": (_int, [_vp, _vp, _int, _vp, _vp]),
+    "csrk_spmv_dev_multi": (_int, [_vp, _vp, _int, _P(_vp), _int, _vp]),
     "csrk_spgemm": (_int, [_vp, _vp, _P(_vp)]),
     "csrk_spgemm_abt": (_int, [_vp, _vp, _P(_vp)]),
     "csrk_spgemm_stats": (_int, [_vp, _P(_i64), _P(_i64)]),

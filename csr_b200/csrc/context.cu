@@ -441,6 +441,18 @@ int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stre
     return spmv_run(h, d_x, x_kind, d_y, s);
 }
 
+int csrk_spmv_dev_multi(csrk_h h, const void *d_x, int x_kind, double *const *d_ys, int n_out, void *stream)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_ARG(x_kind == 4 || x_kind == 8, "x_kind must be 4 or 8 (got %d)", x_kind);
+    CSRK_ARG(n_out >= 1 && n_out <= 8 && d_ys != nullptr, "n_out must be 1..8 (got %d)", n_out);
+    for (int k = 0; k < n_out; k++)
+        CSRK_ARG(h->nrows == 0 || d_ys[k] != nullptr, "y[%d] is NULL", k);
+    CSRK_ARG(h->ncols == 0 || d_x != nullptr, "x is NULL");
+    CSRK_TRY(ensure_init());
+    return spmv_run_multi(h, d_x, x_kind, d_ys, n_out, (cudaStream_t)stream);
+}
+
 int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y)
 {
     CSRK_ARG(h != nullptr, "NULL handle");

@@ -48,6 +48,23 @@ void plan_destroy(SpmvPlan *p, cudaStream_t s)
 
 struct NoVal {};
 
+// Where a finished row goes: p[0] is this GPU's y; p[1..n) are the same segment inside the gather
+// buffers of the peer GPUs (NVLink peer memory), written by the same kernel so that the y
+// all-gather of the row-partitioned SpMV needs no separate collective.
+constexpr int SPMV_MAX_OUT = 8;
+struct YOut {
+    double *p[SPMV_MAX_OUT];
+    int n;
+};
+__device__ __forceinline__ void store_y(const YOut &y, int64_t r, double v)
+{
+    y.p[0][r] = v;
+#pragma unroll
+    for (int k = 1; k < SPMV_MAX_OUT; k++)
+        if (k < y.n)
+            y.p[k][r] = v;
+}
+
 template <typename VT, typename XT> struct Prod {
     using type = double;
 };
@@ -78,7 +95,7 @@ __global__ void k_zero_f64(double *y, int64_t n)
 template <typename RPT, typename VT, typename XT>
 __global__ void __launch_bounds__(SPMV_BLOCK)
 k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_t *__restrict__ ci,
-            const VT *__restrict__ vs, const XT *__restrict__ x, double *__restrict__ y,
+            const VT *__restrict__ vs, const XT *__restrict__ x, YOut y,
             const int32_t *__restrict__ tile_row, double *__restrict__ carry)
 {
     constexpr bool HASV = !std::is_same<VT, NoVal>::value;
@@ -167,7 +184,7 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
             double s = 0.0;
             for (int i = s0; i < e0; i++)
                 s += (double)prod[i];
-            y[r] = s;  // complete row, or the head piece of a row that continues (carries are added later)
+            store_y(y, r, s);  // complete row, or the head piece of a row that continues (carries are added later)
         }
     }
     __syncthreads();
@@ -181,7 +198,7 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
             s += (double)prod[i];
         s = warp_sum(s);
         if ((tid & 31) == 0)
-            y[r] = s;
+            store_y(y, r, s);
     }
 }
 
@@ -189,8 +206,7 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
 // that spills into it, add that row's carries in tile order: deterministic.
 template <typename RPT>
 __global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict__ rp,
-                             const int32_t *__restrict__ tile_row, const double *__restrict__ carry,
-                             double *__restrict__ y)
+                             const int32_t *__restrict__ tile_row, const double *__restrict__ carry, YOut y)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (t >= ntiles)
@@ -208,7 +224,7 @@ __global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict_
     double tot = 0.0;
     for (int64_t u = t; u <= tlast; u++)
         tot += carry[u];
-    y[row] += tot;
+    store_y(y, row, y.p[0][row] + tot);
 }
 
 static int ensure_plan(csrk_matrix *h, cudaStream_t s, SpmvPlan **out)
@@ -250,7 +266,7 @@ static int ensure_plan(csrk_matrix *h, cudaStream_t s, SpmvPlan **out)
 }
 
 template <typename RPT, typename VT, typename XT>
-static int launch_spmv(csrk_matrix *h, SpmvPlan *p, const void *d_x, double *d_y, double *carry, cudaStream_t s)
+static int launch_spmv(csrk_matrix *h, SpmvPlan *p, const void *d_x, YOut d_y, double *carry, cudaStream_t s)
 {
     CSRK_LAUNCH((k_spmv_tile<RPT, VT, XT>), (unsigned)p->ntiles, SPMV_BLOCK, 0, s, h->nrows, h->nnz,
                 (const RPT *)h->rp, h->ci, (const VT *)h->vs, (const XT *)d_x, d_y, p->tile_row, carry);
@@ -261,7 +277,7 @@ static int launch_spmv(csrk_matrix *h, SpmvPlan *p, const void *d_x, double *d_y
 }
 
 template <typename RPT, typename VT>
-static int launch_spmv_x(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kind, double *d_y, double *carry,
+static int launch_spmv_x(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kind, YOut d_y, double *carry,
                          cudaStream_t s)
 {
     if (x_kind == 4)
@@ -270,7 +286,7 @@ static int launch_spmv_x(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kin
 }
 
 template <typename RPT>
-static int launch_spmv_v(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kind, double *d_y, double *carry,
+static int launch_spmv_v(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kind, YOut d_y, double *carry,
                          cudaStream_t s)
 {
     switch (h->val_kind) {
@@ -312,27 +328,41 @@ static int ensure_psf(csrk_matrix *h, int x_kind, PsfPlan **out)
     return CSRK_OK;
 }
 
-int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s)
+int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d_ys, int n_out, cudaStream_t s)
 {
+    YOut yo;
+    yo.n = n_out;
+    for (int k = 0; k < SPMV_MAX_OUT; k++)
+        yo.p[k] = k < n_out ? d_ys[k] : nullptr;
     if (h->nrows == 0)
         return CSRK_OK;
     if (h->nnz == 0) {
-        CSRK_LAUNCH(k_zero_f64, (unsigned)div_up(h->nrows, 256), 256, 0, s, d_y, (int64_t)h->nrows);
+        for (int k = 0; k < n_out; k++)
+            CSRK_LAUNCH(k_zero_f64, (unsigned)div_up(h->nrows, 256), 256, 0, s, d_ys[k], (int64_t)h->nrows);
         return CSRK_OK;
     }
-    if (psf_wanted(h, x_kind, d_x)) {
-        PsfPlan *pp = nullptr;
-        CSRK_TRY(ensure_psf(h, x_kind, &pp));
-        if (pp)
-            return psf_run(h, pp, d_x, d_y, s);
+    if (n_out == 1) {
+        const bool slab = psf_wanted(h, x_kind, d_x);
+        if (slab) {
+            PsfPlan *pp = nullptr;
+            CSRK_TRY(ensure_psf(h, x_kind, &pp));
+            if (pp)
+                return psf_run(h, pp, d_x, d_ys[0], s);
+        }
     }
     SpmvPlan *p = nullptr;
     CSRK_TRY(ensure_plan(h, ctx().stream, &p));
     DevBuf carry;
     CSRK_TRY(carry.alloc(sizeof(double) * (size_t)p->ntiles, s));
     if (h->rp_is64)
-        return launch_spmv_v<int64_t>(h, p, d_x, x_kind, d_y, carry.as<double>(), s);
-    return launch_spmv_v<int32_t>(h, p, d_x, x_kind, d_y, carry.as<double>(), s);
+        return launch_spmv_v<int64_t>(h, p, d_x, x_kind, yo, carry.as<double>(), s);
+    return launch_spmv_v<int32_t>(h, p, d_x, x_kind, yo, carry.as<double>(), s);
+}
+
+int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s)
+{
+    double *ys[1] = {d_y};
+    return spmv_run_multi(h, d_x, x_kind, ys, 1, s);
 }
 
 }  // namespace csrk

@@ -8,9 +8,14 @@ The partition is the parallel form of the reference's sequential sharding
 blocks of about equal nnz, ``split_k = searchsorted(rowptrs, k*nnz/N)``.
 
 * SpMV: every rank holds its row block and a full copy of x.  A step is
-  ``broadcast(x)`` from the root, the local SpMV on the same stream, and an
-  all-gather of the y segments (padded to the longest block; there is no
-  all-gather-v).
+  ``broadcast(x)`` from the root, the local SpMV on the same stream writing into this
+  rank's segment of the gather buffer, and an NCCL all-gather of the y segments (padded
+  to the longest block; there is no all-gather-v).
+  ``fused=True`` replaces SpMV + all-gather by ONE kernel that stores every finished row
+  into this rank's segment of every rank's buffer over NVLink (symmetric memory) plus a
+  barrier.  Measured on 2 B200: 0.547 ms/step fused vs 0.452 ms/step with NCCL (the
+  barrier and the 8-byte-granular peer stores cost more than a 16 MB all-gather), so it
+  is opt-in.
 * SpGEMM (A*B, A*B^T): B is replicated by three broadcasts (rowptrs, colinds,
   values); each rank multiplies its A block; output row blocks stay distributed,
   and ``assemble`` concatenates them on every rank with the int64 rowptr
@@ -58,7 +63,8 @@ class DistSpMV:
     ``row_counts[r]`` is the number of rows rank r owns.
     """
 
-    def __init__(self, local, row_counts, *, x_dtype="f4", device=None, group=None, compute=None, kernel=None):
+    def __init__(self, local, row_counts, *, x_dtype="f4", device=None, group=None, compute=None, kernel=None,
+                 fused=False):
         import torch
         self.torch = torch
         self.group = group
@@ -76,7 +82,13 @@ class DistSpMV:
         tdt = torch.float32 if np.dtype(x_dtype) == np.float32 else torch.float64
         self.x = torch.zeros(self.ncols, dtype=tdt, device=self.device)
         # gather buffer: world segments of `pad` doubles; this rank's SpMV writes straight into its segment
-        self.ybuf = torch.zeros(self.world * self.pad, dtype=torch.float64, device=self.device)
+        self.ybuf = None
+        self.symm = None          # symmetric-memory handle when the fused gather is active
+        self.peer_ptrs = None
+        if fused and compute is None and self.world > 1 and self.world <= 8 and self.device.type == "cuda":
+            self._setup_fused(group)
+        if self.ybuf is None:
+            self.ybuf = torch.zeros(self.world * self.pad, dtype=torch.float64, device=self.device)
         self.handle = None
         if compute is None:
             if kernel is None:
@@ -86,6 +98,29 @@ class DistSpMV:
             self.handle = kernel.to_handle(local)
             compute = self._cuda_compute
         self.compute = compute
+
+    def _setup_fused(self, group):
+        """Fused compute + collective: the gather buffer lives in symmetric memory (NVLink peer
+        mappings set up by torch.distributed), and the SpMV kernel stores every finished row
+        into this rank's segment of EVERY rank's buffer.  The NCCL all-gather becomes a barrier."""
+        torch = self.torch
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            dist = _dist()
+            g = group if group is not None else dist.group.WORLD
+            buf = symm_mem.empty(self.world * self.pad, dtype=torch.float64, device=self.device)
+            hdl = symm_mem.rendezvous(buf, g)
+            buf.zero_()
+            off = self.rank * self.pad * 8
+            ptrs = [int(p) + off for p in hdl.buffer_ptrs]
+            # local first, then the peers
+            self.peer_ptrs = [ptrs[self.rank]] + [ptrs[r] for r in range(self.world) if r != self.rank]
+            self.ybuf, self.symm = buf, hdl
+            torch.cuda.synchronize()
+            hdl.barrier()
+        except Exception as e:  # no P2P / symmetric memory: keep the NCCL all-gather
+            self.ybuf, self.symm, self.peer_ptrs = None, None, None
+            self.fused_error = repr(e)
 
     def _cuda_compute(self, x, y):
         stream = self.torch.cuda.current_stream().cuda_stream
@@ -101,6 +136,12 @@ class DistSpMV:
         dist = _dist()
         if self.world > 1 and broadcast_x:
             dist.broadcast(self.x, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+        if self.symm is not None:
+            # one kernel computes the rows and scatters them to every rank over NVLink
+            stream = self.torch.cuda.current_stream().cuda_stream
+            self.kernel.mult_vec_dev_multi(self.handle, self.x.data_ptr(), self.x.element_size(), self.peer_ptrs, stream)
+            self.symm.barrier()   # all ranks' segments have landed everywhere
+            return self.ybuf
         seg = self.ybuf[self.rank * self.pad: self.rank * self.pad + self.row_counts[self.rank]]
         self.compute(self.x, seg)
         if self.world > 1:

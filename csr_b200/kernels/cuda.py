@@ -226,6 +226,14 @@ def mult_vec_dev(h: cuda_h, x_ptr: int, x_itemsize: int, y_ptr: int, stream: int
                                   C.c_void_p(stream)), "mult_vec_dev")
 
 
+def mult_vec_dev_multi(h: cuda_h, x_ptr: int, x_itemsize: int, y_ptrs, stream: int = 0) -> None:
+    """Fused SpMV + gather: like :func:`mult_vec_dev`, but every finished row is stored to all
+    of ``y_ptrs`` (``y_ptrs[0]`` local, the rest the same segment in peer GPUs' buffers)."""
+    arr = (C.c_void_p * len(y_ptrs))(*[C.c_void_p(int(p)) for p in y_ptrs])
+    N.check(N.lib().csrk_spmv_dev_multi(_live(h), C.c_void_p(x_ptr), int(x_itemsize), arr, len(y_ptrs),
+                                        C.c_void_p(stream)), "mult_vec_dev_multi")
+
+
 def from_device_arrays(nrows, ncols, nnz, rowptrs_ptr, rp_is64, colinds_ptr, values_ptr, val_kind,
                        stream: int = 0, csr_cls=None) -> cuda_h:
     """Build a handle from device arrays (D2D copy)."""

@@ -99,6 +99,10 @@ int csrk_subset_rows(csrk_h h, int32_t begin, int32_t end, csrk_h *out);
 int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y);
 /* Device pointers; y has nrows doubles. */
 int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stream);
+/* Fused SpMV + gather for the row-partitioned multi-GPU SpMV: every finished row is stored to
+ * d_ys[0] (this GPU) AND to d_ys[1..n_out) (the same y segment inside the peers' gather buffers,
+ * NVLink peer / symmetric memory), n_out <= 8.  d_ys is a HOST array of device pointers. */
+int csrk_spmv_dev_multi(csrk_h h, const void *d_x, int x_kind, double *const *d_ys, int n_out, void *stream);
 
 /* ---- mult_ab / mult_abt: multiply.py:13-57; lk_mkl_spmab/spmabt ----------
  * C = A*B (a.ncols == b.nrows) and C = A*B^T (a.ncols == b.ncols) as a NEW
