@@ -174,7 +174,7 @@ def run_ours(args):
     x_host = np.random.default_rng(77).standard_normal(A.ncols).astype(np.float32)
     row_counts = [A.nrows] * world
     t0 = time.perf_counter()
-    ds = DistSpMV(A, row_counts, x_dtype="f4", kernel=K, fused=args.fused)
+    ds = DistSpMV(A, row_counts, x_dtype="f4", kernel=K, fused=args.fused, chunks=args.chunks if world > 1 else 1)
     t_handle = time.perf_counter() - t0
     ds.set_x(x_host)
     log(f"[rank {rank}] block {A}  gen {t_gen:.1f}s  to_handle {t_handle:.2f}s")
@@ -220,13 +220,12 @@ def run_ours(args):
 
     # ---- the dominant kernel alone (local SpMV, no collectives) for the roofline
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    seg = ds.ybuf[ds.rank * ds.pad: ds.rank * ds.pad + A.nrows]
     for _ in range(3):
-        ds.compute(ds.x, seg)
+        ds.local_spmv()
     torch.cuda.synchronize()
     e2.record()
     for _ in range(steps):
-        ds.compute(ds.x, seg)
+        ds.local_spmv()
     e3.record()
     torch.cuda.synchronize()
     ms_kernel = e2.elapsed_time(e3) / steps
@@ -237,19 +236,25 @@ def run_ours(args):
     xp.copy_(torch.from_numpy(x_host))
     yp = torch.empty(A.nrows, dtype=torch.float64).pin_memory()
     xn, yn = xp.numpy(), yp.numpy()
+    h_e2e = ds.handle if ds.chunks == 1 else K.to_handle(A)   # the public call works on one handle
     for _ in range(W):
-        K.mult_vec(ds.handle, xn, out=yn)
+        K.mult_vec(h_e2e, xn, out=yn)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        K.mult_vec(ds.handle, xn, out=yn)
+        K.mult_vec(h_e2e, xn, out=yn)
     e2e_s = allmax((time.perf_counter() - t0) / steps)
     barrier()
     e2e_val = total_bytes / e2e_s / 1e9
 
     # sanity: the timed path computes the right thing (size-independent check on a sample of rows)
-    y_dev = ds.ybuf[ds.rank * ds.pad: ds.rank * ds.pad + A.nrows].cpu().numpy()
+    ds.step()
+    torch.cuda.synchronize()
+    y_all = ds.result()
+    y_dev = y_all[rank * A.nrows:(rank + 1) * A.nrows]
     assert np.allclose(y_dev, yn, rtol=1e-9, atol=1e-9), "device-resident and host-API results differ"
+    if h_e2e is not ds.handle:
+        K.release_handle(h_e2e)
 
     out = {
         "metric": "spmv_hbm_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": steps,
@@ -263,7 +268,8 @@ def run_ours(args):
             "columns": "stratified uniform" if args.col_skew == 1.0 else f"stratified, skew t^{args.col_skew}",
             "parallelism": f"row-partitioned x{world}; step = NCCL broadcast(x) + " + (
                 "SpMV kernel storing y rows into every rank's buffer over NVLink (fused gather) + barrier"
-                if ds.symm is not None else "local SpMV + NCCL all-gather(y)"),
+                if ds.symm is not None else
+                f"local SpMV + NCCL all-gather(y) in {ds.chunks} row chunks, each gather overlapping the next chunk's SpMV"),
             "l2_policy": "inputs (>=0.8 GB per GPU) larger than the 126 MB L2; no flush needed",
             "bytes_per_step": int(total_bytes), "scale": args.scale,
         },
@@ -467,6 +473,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only)")
     ap.add_argument("--col-skew", type=float, default=1.0)
     ap.add_argument("--spgemm-scale", type=float, default=1.0, help="scale of configs[2] for the A*A^T leg (0 = skip)")
+    ap.add_argument("--chunks", type=int, default=1, help="N>1: row chunks whose all-gathers overlap the next chunk's SpMV")
     ap.add_argument("--fused", action="store_true", help="fused SpMV+gather over peer memory instead of the NCCL all-gather")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the SpMV kernel, if known")
     args = ap.parse_args()

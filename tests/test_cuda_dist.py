@@ -45,7 +45,18 @@ def _worker(rank, world, port, q):
             ds.close()
         yf, was_fused = out[True]
         yn, _ = out[False]
-        ok = bool(np.allclose(yf, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max()) and np.array_equal(yf, yn))
+        # pipelined: 4 row chunks, each all-gather overlapping the next chunk's SpMV
+        ds = DistSpMV(mine, counts, x_dtype="f4", chunks=4)
+        if rank == 0:
+            ds.set_x(x)
+        for _ in range(3):
+            ds.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        yc = ds.result()
+        ds.close()
+        tol = dict(rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+        ok = bool(np.allclose(yf, ref, **tol) and np.array_equal(yf, yn) and np.allclose(yc, ref, **tol))
         q.put((rank, ok, was_fused))
     finally:
         dist.destroy_process_group()

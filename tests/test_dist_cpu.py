@@ -49,6 +49,16 @@ def _worker(rank, world, port, q):
         ref = orc.mult_vec(A, x)
         ok_spmv = bool(np.array_equal(y, ref))
 
+        # pipelined variant: two row chunks per rank, chunk gathers launched asynchronously
+        def compute_rows(x, y, r0, r1):
+            y.copy_(torch.from_numpy(orc.mult_vec(mine.subset_rows(r0, r1), x.numpy())))
+
+        ds2 = DistSpMV(mine, counts, x_dtype="f8", device=torch.device("cpu"), compute=compute_rows, chunks=2)
+        if rank == 0:
+            ds2.set_x(x)
+        ds2.step()
+        ok_spmv = ok_spmv and bool(np.array_equal(ds2.result(), ref))
+
         # SpGEMM: B known on rank 0 only, replicated by broadcast; A row blocks; assemble
         B = synth.powerlaw_csr(500, 300, 6000, seed=6, dtype="f8", alpha=0.7) if rank == 0 else None
         Brep = replicate_csr(B, src=0, device=torch.device("cpu"))
