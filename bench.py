@@ -231,6 +231,26 @@ def run_ours(args):
     ms_kernel = e2.elapsed_time(e3) / steps
     achieved = local_bytes / (ms_kernel * 1e-3) / 1e9
 
+    # ---- N>1: what the two collectives cost on their own (same buffers, same stream)
+    coll = None
+    if world > 1 and ds.symm is None:
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return allmax(a.elapsed_time(b) / steps)
+        t_b = timed(lambda: dist.broadcast(ds.x, src=0))
+        t_g = timed(lambda: dist.all_gather_into_tensor(ds.ybuf[ds.coff[0]:ds.coff[1]], ds._seg(0)))
+        coll = {"broadcast_x_ms": round(t_b, 5), "broadcast_x_bytes": int(ds.x.numel() * ds.x.element_size()),
+                "all_gather_y_ms": round(t_g, 5), "all_gather_y_bytes": int((ds.coff[1] - ds.coff[0]) * 8),
+                "note": "NCCL over NVLink/NVSwitch, timed alone; in a step they run back to back with the SpMV"}
+
     # ---- e2e: public kernel call, host (pinned) x and y
     xp = torch.empty(A.ncols, dtype=torch.float32).pin_memory()
     xp.copy_(torch.from_numpy(x_host))
@@ -284,6 +304,8 @@ def run_ours(args):
                      "frac_of_nominal_8000": round(achieved / 8000.0, 4)},
         "clocks": clk.summary(),
     }
+    if coll is not None:
+        out["collectives"] = coll
 
     if world == 1 and rank == 0:
         out["cpu_baseline"] = cpu_baseline_spmv(A, x_host, yn)

@@ -23,8 +23,7 @@
 #include <algorithm>
 #include <type_traits>
 
-#include "common.cuh"
-#include "scan.cuh"
+#include "radix.cuh"
 
 namespace csrk {
 
@@ -781,6 +780,16 @@ k_num_owner(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
     }
 }
 
+// sort key for longest-processing-time-first scheduling of the heavy rows: descending products
+__global__ void k_lpt_keys(const int32_t *__restrict__ rows, int n, const int64_t *__restrict__ prod, int32_t *__restrict__ keys)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t p = prod[rows[i]] >> 6;
+        keys[i] = 0x7FFFFFFF - (int32_t)(p > 0x7FFFFFFF ? 0x7FFFFFFF : p);
+    }
+}
+
 template <typename T> __global__ void k_narrow_rp(const int64_t *__restrict__ in, T *__restrict__ out, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -939,6 +948,28 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
         else
             k_narrow_rp<int32_t><<<grid, 256, 0, s>>>(rp64.as<int64_t>(), (int32_t *)out->rp, (int64_t)m + 1);
         g_launches.fetch_add(1);
+    }
+
+    // heavy rows are handed to the persistent CTAs most expensive first (LPT): with dynamic
+    // scheduling the tail of the kernel is then made of cheap rows
+    DevBuf lpt_keys, lpt_rows;
+    if (ncnt[5] > 1) {
+        rc = lpt_keys.alloc(sizeof(int32_t) * (size_t)ncnt[5], s);
+        if (rc == CSRK_OK)
+            rc = lpt_rows.alloc(sizeof(int32_t) * (size_t)ncnt[5], s);
+        if (rc != CSRK_OK)
+            return fail(rc);
+        k_lpt_keys<<<(unsigned)div_up(ncnt[5], 256), 256, 0, s>>>(nlist.as<int32_t>() + noff[5], ncnt[5], prod.as<int64_t>(),
+                                                                   lpt_keys.as<int32_t>());
+        g_launches.fetch_add(1);
+        rc = radix_sort_by_key<NoPayload>(lpt_keys.as<int32_t>(), nlist.as<int32_t>() + noff[5], (const NoPayload *)nullptr,
+                                          (int64_t)ncnt[5], 31, lpt_rows.as<int32_t>(), (NoPayload *)nullptr, s);
+        if (rc != CSRK_OK)
+            return fail(rc);
+        cudaError_t ce = cudaMemcpyAsync(nlist.as<int32_t>() + noff[5], lpt_rows.p, sizeof(int32_t) * (size_t)ncnt[5],
+                                         cudaMemcpyDeviceToDevice, s);
+        if (ce != cudaSuccess)
+            return fail(cuda_fail(ce, "lpt copy", __FILE__, __LINE__));
     }
 
     // ---- step 3: numeric
