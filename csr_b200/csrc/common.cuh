@@ -93,10 +93,11 @@ void dev_free(void *p, cudaStream_t s);
 // ------------------------------------------------------------------ matrix
 struct SpmvPlan;  // spmv.cu: tile map of the CSR kernel
 struct PsfPlan;   // spmv_psf.cu: panel/slab re-layout for large matrices
+struct Psf3Plan;  // spmv_psf3.cu: cell-tile slab kernel with TMA-staged entries
 
 // tunables settable through csrk_set_option (tests force the slab path on small inputs)
 struct Options {
-    std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab kernel
+    std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab kernel v1, 3 cell-tile slab kernel
     std::atomic<int64_t> psf_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a slab plan
     std::atomic<int64_t> own_nw{16};                    // warps (column ranges) per CTA in the owner-computes SpGEMM
 };
@@ -117,6 +118,8 @@ struct csrk_matrix {
     csrk::SpmvPlan *plan = nullptr;  // lazily built SpMV tile map
     csrk::PsfPlan *psf[2] = {nullptr, nullptr};  // lazily built slab plans for float32 / float64 x
     bool psf_failed[2] = {false, false};
+    csrk::Psf3Plan *psf3[2] = {nullptr, nullptr};
+    bool psf3_failed[2] = {false, false};
     std::mutex mu;
 };
 
@@ -131,6 +134,10 @@ void psf_destroy(PsfPlan *p, cudaStream_t s);
 int psf_build(csrk_matrix *h, int x_kind, PsfPlan **out, cudaStream_t s);  // syncs internally
 int psf_run(csrk_matrix *h, PsfPlan *p, const void *d_x, double *d_y, cudaStream_t s);
 int psf_panels(const PsfPlan *p);
+void psf3_destroy(Psf3Plan *p, cudaStream_t s);
+bool psf3_supported(const csrk_matrix *h, int x_kind);
+int psf3_build(csrk_matrix *h, int x_kind, Psf3Plan **out, cudaStream_t s);  // syncs internally
+int psf3_run(csrk_matrix *h, Psf3Plan *p, const void *d_x, double *d_y, cudaStream_t s);
 
 // ops implemented across the .cu files (all enqueue on `s`, no sync unless stated)
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s);

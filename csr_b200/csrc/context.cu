@@ -176,6 +176,8 @@ void matrix_destroy(csrk_matrix *m, cudaStream_t s)
     plan_destroy(m->plan, s);
     psf_destroy(m->psf[0], s);
     psf_destroy(m->psf[1], s);
+    psf3_destroy(m->psf3[0], s);
+    psf3_destroy(m->psf3[1], s);
     delete m;
 }
 
@@ -188,6 +190,9 @@ void plan_invalidate(csrk_matrix *m, cudaStream_t s)
         psf_destroy(m->psf[k], s);
         m->psf[k] = nullptr;
         m->psf_failed[k] = false;
+        psf3_destroy(m->psf3[k], s);
+        m->psf3[k] = nullptr;
+        m->psf3_failed[k] = false;
     }
 }
 
@@ -257,7 +262,7 @@ int csrk_set_option(const char *name, int64_t value)
 {
     CSRK_ARG(name != nullptr, "option name is NULL");
     if (!strcmp(name, "spmv_mode")) {
-        CSRK_ARG(value >= 0 && value <= 2, "spmv_mode must be 0 (auto), 1 (tile) or 2 (slab)");
+        CSRK_ARG(value >= 0 && value <= 3, "spmv_mode must be 0 (auto), 1 (tile), 2 (slab v1) or 3 (cell-tile slab)");
         options().spmv_mode = value;
     } else if (!strcmp(name, "psf_min_nnz")) {
         options().psf_min_nnz = value;

@@ -308,6 +308,26 @@ static bool psf_wanted(const csrk_matrix *h, int x_kind, const void *d_x)
     return nslabs <= 4096 && h->nnz < ((int64_t)1 << 33);
 }
 
+static int ensure_psf3(csrk_matrix *h, int x_kind, Psf3Plan **out)
+{
+    const int k = x_kind == 4 ? 0 : 1;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->psf3[k] && !h->psf3_failed[k]) {
+        Psf3Plan *p = nullptr;
+        const int rc = psf3_build(h, x_kind, &p, ctx().stream);
+        if (rc == CSRK_EOVERFLOW) {
+            h->psf3_failed[k] = true;
+            return CSRK_OK;
+        }
+        if (rc != CSRK_OK)
+            return rc;
+        h->psf3[k] = p;
+    }
+    *out = h->psf3[k];
+    return CSRK_OK;
+}
+
 static int ensure_psf(csrk_matrix *h, int x_kind, PsfPlan **out)
 {
     const int k = x_kind == 4 ? 0 : 1;
@@ -342,12 +362,18 @@ int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d
         return CSRK_OK;
     }
     if (n_out == 1) {
-        const bool slab = psf_wanted(h, x_kind, d_x);
-        if (slab) {
+        const int64_t mode = options().spmv_mode.load();
+        if (mode == 2 && psf_wanted(h, x_kind, d_x)) {
             PsfPlan *pp = nullptr;
             CSRK_TRY(ensure_psf(h, x_kind, &pp));
             if (pp)
                 return psf_run(h, pp, d_x, d_ys[0], s);
+        } else if (mode == 3 && ((uintptr_t)d_x & 15) == 0 && psf3_supported(h, x_kind) &&
+                   div_up((int64_t)h->ncols * x_kind, 32 * 1024) <= 60000 && h->nnz < ((int64_t)1 << 33)) {
+            Psf3Plan *pp = nullptr;
+            CSRK_TRY(ensure_psf3(h, x_kind, &pp));
+            if (pp)
+                return psf3_run(h, pp, d_x, d_ys[0], s);
         }
     }
     SpmvPlan *p = nullptr;

@@ -1,5 +1,5 @@
 """
-GPU: the panel/slab SpMV (csr_b200/csrc/spmv_psf.cu), forced on through the
+GPU: the panel/slab SpMV kernels (csr_b200/csrc/spmv_psf.cu, spmv_psf3.cu), forced on through the
 ``spmv_mode`` option so that small inputs exercise it, against the golden vectors,
 the oracle and the CSR tile kernel.
 """
@@ -18,9 +18,12 @@ pytestmark = pytest.mark.gpu
 _Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
 
 
-@pytest.fixture()
-def slab(kernel):
-    kernel.set_option("spmv_mode", 2)
+@pytest.fixture(params=[2, 3], ids=["v1", "celltile"])
+def slab(kernel, request):
+    """Both slab designs: 2 = spmv_psf.cu, 3 = spmv_psf3.cu (cell-tile, TMA-staged entries; dtype
+    combinations it does not cover fall back to the CSR tile kernel)."""
+    kernel.set_option("spmv_mode", request.param)
+    kernel._slab_mode = request.param
     try:
         yield kernel
     finally:
@@ -96,7 +99,7 @@ def test_matches_tile_kernel_and_nonfinite(slab):
     y = _run(slab, A, x)
     slab.set_option("spmv_mode", 1)
     yt = _run(slab, A, x)
-    slab.set_option("spmv_mode", 2)
+    slab.set_option("spmv_mode", slab._slab_mode)
     bad = ~np.isfinite(yt)
     assert np.array_equal(~np.isfinite(y), bad), "inf/nan must propagate to exactly the same rows"
     assert np.array_equal(np.isnan(y), np.isnan(yt))

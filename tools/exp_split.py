@@ -34,6 +34,6 @@ def subset(mask):
 H = subset(lens > TH); L = subset(lens <= TH)
 print("heavy", H, "light", L, flush=True)
 for name, M in (("full", A), ("heavy", H), ("light", L)):
-    for mode, mn in ((1, "tile"), (2, "slab")):
+    for mode, mn in ((1, "tile"), (3, "cell")):
         ms, gbs = bench(M, x, mode)
         print(f"{name:6s} {mn:5s} {ms*1000:8.1f} us  {gbs:8.1f} GB/s", flush=True)
