@@ -11,6 +11,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "csrk.h"
 
@@ -57,6 +58,17 @@ int ensure_init();  // CSRK_OK once csrk_init has run (auto-inits device 0 / $LO
 
 extern std::atomic<int64_t> g_launches;
 
+// CSRK_TRACE=1 in the environment prints "[csrk] <label> <ms>" lines to stderr at the phase marks
+// below (each mark synchronises the stream, so traced runs are slower); the analogue of the
+// reference shim's compile-time LK_TRACE (csr/kernels/mkl/mkl_ops.c:57-59).
+bool trace_enabled();
+void trace_mark(const char *label, cudaStream_t s);
+#define CSRK_TRACE_MARK(label, s)                                                \
+    do {                                                                         \
+        if (::csrk::trace_enabled())                                             \
+            ::csrk::trace_mark(label, s);                                        \
+    } while (0)
+
 // every kernel launch goes through this so csrk_launch_count() is exact
 #define CSRK_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
     do {                                                                         \
@@ -65,17 +77,36 @@ extern std::atomic<int64_t> g_launches;
         CSRK_CUDA(cudaGetLastError());                                           \
     } while (0)
 
+// ------------------------------------------------------------ workspace arena
+// Temporaries of the multi-kernel operations (transpose, SpGEMM, filter, plan builds) are bump-
+// allocated from device chunks that are kept for the life of the library and rewound when the
+// operation ends.  Churning multi-hundred-MB temporaries of varying sizes through the
+// stream-ordered pool made it re-map physical memory at random (a 100M-nnz transpose took
+// 15 ms or 170 ms); outputs owned by a handle still come from cudaMallocAsync.
+// A WsScope serialises the operations that use the arena (they share the library stream anyway).
+struct WsScope {
+    WsScope();
+    ~WsScope();
+    WsScope(const WsScope &) = delete;
+    WsScope &operator=(const WsScope &) = delete;
+    std::vector<size_t> marks;
+};
+void ws_release_all();         // csrk_shutdown
+void *ws_alloc(size_t bytes);  // nullptr if no scope is active on this thread or the device is out of memory
+
 // ------------------------------------------------- stream-ordered device buffer
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     cudaStream_t s = nullptr;
+    bool from_ws = false;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { reset(); }
-    int alloc(size_t nbytes, cudaStream_t stream);
+    int alloc(size_t nbytes, cudaStream_t stream);       // temporary: workspace arena when a WsScope is active
     int alloc_zero(size_t nbytes, cudaStream_t stream);
+    int alloc_owned(size_t nbytes, cudaStream_t stream);  // from the pool: may be release()d into a handle
     void reset();
     void *release()
     {

@@ -6,6 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <chrono>
+
 #include "common.cuh"
 
 namespace csrk {
@@ -37,6 +40,24 @@ Context &ctx()
 {
     static Context c;
     return c;
+}
+
+bool trace_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("CSRK_TRACE");
+        return e && *e && *e != '0';
+    }();
+    return on;
+}
+
+void trace_mark(const char *label, cudaStream_t s)
+{
+    static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[csrk] %-28s %9.3f ms\n", label, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
 }
 
 Options &options()
@@ -116,7 +137,95 @@ void dev_free(void *p, cudaStream_t s)
         (void)cudaFreeAsync(p, s);
 }
 
+// ---- workspace arena
+namespace {
+struct WsChunk {
+    char *p;
+    size_t cap, top;
+};
+struct Workspace {
+    std::vector<WsChunk> chunks;
+    std::recursive_mutex mu;
+};
+Workspace &ws()
+{
+    static Workspace w;
+    return w;
+}
+thread_local int t_ws_depth = 0;
+}  // namespace
+
+WsScope::WsScope()
+{
+    ws().mu.lock();
+    t_ws_depth++;
+    for (auto &c : ws().chunks)
+        marks.push_back(c.top);
+}
+
+WsScope::~WsScope()
+{
+    auto &ch = ws().chunks;
+    for (size_t i = 0; i < ch.size(); i++)
+        ch[i].top = i < marks.size() ? marks[i] : 0;
+    t_ws_depth--;
+    ws().mu.unlock();
+}
+
+void ws_release_all()
+{
+    std::lock_guard<std::recursive_mutex> g(ws().mu);
+    for (auto &c : ws().chunks)
+        (void)cudaFree(c.p);
+    ws().chunks.clear();
+}
+
+void *ws_alloc(size_t bytes)
+{
+    if (t_ws_depth == 0)
+        return nullptr;
+    bytes = (bytes + 511) & ~(size_t)511;
+    if (bytes == 0)
+        bytes = 512;
+    auto &ch = ws().chunks;
+    for (auto &c : ch) {
+        if (c.cap - c.top >= bytes) {
+            void *p = c.p + c.top;
+            c.top += bytes;
+            return p;
+        }
+    }
+    // new chunk: at least 256 MB, or the request rounded up to 64 MB
+    size_t cap = std::max<size_t>((size_t)256 << 20, (bytes + ((size_t)64 << 20) - 1) & ~(((size_t)64 << 20) - 1));
+    void *p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cap = bytes;
+        if (cudaMalloc(&p, cap) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+    }
+    ch.push_back(WsChunk{(char *)p, cap, bytes});
+    return p;
+}
+
 int DevBuf::alloc(size_t nbytes, cudaStream_t stream)
+{
+    reset();
+    s = stream;
+    if (void *q = ws_alloc(nbytes)) {
+        p = q;
+        from_ws = true;
+        bytes = nbytes;
+        return CSRK_OK;
+    }
+    CSRK_TRY(dev_alloc(&p, nbytes, stream));
+    bytes = nbytes;
+    return CSRK_OK;
+}
+
+int DevBuf::alloc_owned(size_t nbytes, cudaStream_t stream)
 {
     reset();
     s = stream;
@@ -134,10 +243,11 @@ int DevBuf::alloc_zero(size_t nbytes, cudaStream_t stream)
 
 void DevBuf::reset()
 {
-    if (p)
+    if (p && !from_ws)
         dev_free(p, s);
     p = nullptr;
     bytes = 0;
+    from_ws = false;
 }
 
 int matrix_alloc(csrk_matrix **out, int32_t nrows, int32_t ncols, int64_t nnz, int rp_is64, int val_kind, cudaStream_t s)
@@ -237,6 +347,7 @@ int csrk_shutdown(void)
         return CSRK_OK;
     CSRK_CUDA(cudaSetDevice(c.device));
     CSRK_CUDA(cudaStreamSynchronize(c.stream));
+    ws_release_all();
     CSRK_CUDA(cudaStreamDestroy(c.stream));
     c.stream = nullptr;
     c.inited = false;
@@ -483,6 +594,7 @@ int csrk_spgemm(csrk_h a, csrk_h b, csrk_h *c)
     CSRK_ARG(a && b && c, "NULL handle");
     CSRK_ARG(a->ncols == b->nrows, "mult_ab: a.ncols (%d) != b.nrows (%d)", a->ncols, b->nrows);
     CSRK_TRY(ensure_init());
+    WsScope scope;
     return spgemm_run(a, b, c, ctx().stream);
 }
 
@@ -492,6 +604,7 @@ int csrk_spgemm_abt(csrk_h a, csrk_h b, csrk_h *c)
     CSRK_ARG(a->ncols == b->ncols, "mult_abt: a.ncols (%d) != b.ncols (%d)", a->ncols, b->ncols);
     CSRK_TRY(ensure_init());
     cudaStream_t s = ctx().stream;
+    WsScope scope;
     // multiply.py:56-57: bt = b.transpose(); mult_ab(a, bt)
     csrk_matrix *bt = nullptr;
     CSRK_TRY(transpose_run(b, 1, &bt, s));
@@ -512,6 +625,7 @@ int csrk_transpose(csrk_h a, int with_values, csrk_h *at)
 {
     CSRK_ARG(a && at, "NULL handle");
     CSRK_TRY(ensure_init());
+    WsScope scope;
     return transpose_run(a, with_values, at, ctx().stream);
 }
 
@@ -519,6 +633,7 @@ int csrk_order_columns(csrk_h h)
 {
     CSRK_ARG(h != nullptr, "NULL handle");
     CSRK_TRY(ensure_init());
+    WsScope scope;
     return order_columns_run(h, ctx().stream);
 }
 
@@ -526,6 +641,7 @@ int csrk_filter_zeros(csrk_h h)
 {
     CSRK_ARG(h != nullptr, "NULL handle");
     CSRK_TRY(ensure_init());
+    WsScope scope;
     return filter_zeros_run(h, ctx().stream);
 }
 

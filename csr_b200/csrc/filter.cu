@@ -44,8 +44,8 @@ template <typename VT> static int filter_typed(csrk_matrix *h, cudaStream_t s)
     if (kept == nnz)
         return CSRK_OK;  // nothing stored is zero
     DevBuf ci2, vs2;
-    CSRK_TRY(ci2.alloc(sizeof(int32_t) * (size_t)kept, s));
-    CSRK_TRY(vs2.alloc(sizeof(VT) * (size_t)kept, s));
+    CSRK_TRY(ci2.alloc_owned(sizeof(int32_t) * (size_t)kept, s));
+    CSRK_TRY(vs2.alloc_owned(sizeof(VT) * (size_t)kept, s));
     CSRK_LAUNCH((k_filter_scatter<VT>), (unsigned)div_up(nnz, 256), 256, 0, s, h->ci, (const VT *)h->vs, nnz,
                 pos.as<int64_t>(), ci2.as<int32_t>(), vs2.as<VT>());
     const unsigned grid = (unsigned)div_up((int64_t)h->nrows + 1, 256);

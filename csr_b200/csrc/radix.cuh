@@ -139,6 +139,7 @@ static int radix_sort_by_key(const int32_t *keys, const int32_t *rows, const VT 
     }
     CSRK_TRY(hist.alloc(sizeof(uint32_t) * 256 * (size_t)ntiles, s));
     CSRK_TRY(offs.alloc(sizeof(int64_t) * (256 * (size_t)ntiles + 1), s));
+    CSRK_TRACE_MARK("  sort: buffers allocated", s);
     const int32_t *kin = keys;
     const int32_t *rin = rows;
     const VT *vin = vals;
@@ -152,6 +153,7 @@ static int radix_sort_by_key(const int32_t *keys, const int32_t *rows, const VT 
         kin = kout;
         rin = rout;
         vin = vout;
+        CSRK_TRACE_MARK("  sort: pass", s);
     }
     return CSRK_OK;
 }

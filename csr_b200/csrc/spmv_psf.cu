@@ -629,6 +629,7 @@ int psf_build(csrk_matrix *h, int x_kind, PsfPlan **out, cudaStream_t s)
         set_error("host allocation failed");
         return CSRK_ENOMEM;
     }
+    WsScope scope;  // build temporaries come from the workspace arena
     P->x_kind = x_kind;
     PsfCfg &c = P->cfg;
     c.logw = x_kind == 4 ? 14 : 13;

@@ -658,6 +658,7 @@ int psf3_build(csrk_matrix *h, int x_kind, Psf3Plan **out, cudaStream_t s)
         set_error("host allocation failed");
         return CSRK_ENOMEM;
     }
+    WsScope scope;  // build temporaries come from the workspace arena
     P->x_kind = x_kind;
     P->val_kind = h->val_kind;
     P3Cfg &c = P->cfg;

@@ -83,28 +83,32 @@ static int transpose_core(int32_t nrows, int32_t ncols, int64_t nnz, const RPT *
 {
     constexpr bool HASV = !std::is_same<VT, NoPayload>::value;
     using CT = typename std::conditional<sizeof(RPT) == 8, unsigned long long, int>::type;
+    CSRK_TRACE_MARK("transpose: enter", s);
     // 1. column counts -> output rowptrs
     DevBuf cnt;
     CSRK_TRY(cnt.alloc_zero(sizeof(RPT) * ((size_t)ncols + 1), s));
-    CSRK_TRY(out.rp.alloc(sizeof(RPT) * ((size_t)ncols + 1), s));
+    CSRK_TRY(out.rp.alloc_owned(sizeof(RPT) * ((size_t)ncols + 1), s));
     if (nnz)
         CSRK_LAUNCH((k_col_count<CT>), (unsigned)div_up(nnz, 256), 256, 0, s, ci, nnz, cnt.as<CT>());
     CSRK_TRY((exclusive_scan<RPT>(ArrayLoader<RPT>{cnt.as<RPT>()}, (int64_t)ncols, out.rp.as<RPT>(), s)));
     cnt.reset();
-    CSRK_TRY(out.ci.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    CSRK_TRY(out.ci.alloc_owned(sizeof(int32_t) * (size_t)nnz, s));
     if (HASV)
-        CSRK_TRY(out.vs.alloc(sizeof(VT) * (size_t)nnz, s));
+        CSRK_TRY(out.vs.alloc_owned(sizeof(VT) * (size_t)nnz, s));
     if (nnz == 0)
         return CSRK_OK;
+    CSRK_TRACE_MARK("transpose: counts+scan+alloc", s);
 
     // 2. source row of every entry
     DevBuf rows0;
     CSRK_TRY(rows0.alloc(sizeof(int32_t) * (size_t)nnz, s));
     CSRK_LAUNCH((k_expand_rows<RPT>), (unsigned)div_up(nnz, 256), 256, 0, s, rp, nrows, nnz, rows0.as<int32_t>());
 
+    CSRK_TRACE_MARK("transpose: expand rows", s);
     // 3. stable LSD radix sort by column; the payloads land in out.ci / out.vs
     CSRK_TRY((radix_sort_by_key<VT>(ci, rows0.as<int32_t>(), vs, nnz, key_bits(ncols), out.ci.as<int32_t>(),
                                     HASV ? out.vs.as<VT>() : nullptr, s)));
+    CSRK_TRACE_MARK("transpose: radix sort", s);
     return CSRK_OK;
 }
 
@@ -140,7 +144,7 @@ int transpose_run(csrk_matrix *a, int with_values, csrk_matrix **result, cudaStr
     m->val_kind = vk ? 8 : 0;  // structure.py:177: transposed values are always float64
     if (vk == 4) {
         DevBuf v64;
-        int rc = v64.alloc(sizeof(double) * (size_t)a->nnz, s);
+        int rc = v64.alloc_owned(sizeof(double) * (size_t)a->nnz, s);
         if (rc != CSRK_OK) {
             delete m;
             return rc;
