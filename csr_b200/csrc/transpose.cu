@@ -19,23 +19,94 @@
 
 namespace csrk {
 
-// rows[i] = the row that owns nnz position i (last r with rp[r] <= i)
+// rows[i] = the row that owns nnz position i (last r with rp[r] <= i).
+// One CTA per tile of EXP_TILE consecutive positions: the rows that start inside the tile mark
+// their first position in shared memory (empty rows collide on one position; the largest wins,
+// which is the owner), a running maximum over the tile fills the gaps.  Two binary searches per
+// tile instead of one per entry.
+constexpr int EXP_TILE = 4096;
 template <typename RPT>
-__global__ void k_expand_rows(const RPT *__restrict__ rp, int32_t nrows, int64_t nnz, int32_t *__restrict__ rows)
+__global__ void __launch_bounds__(256)
+k_expand_rows(const RPT *__restrict__ rp, int32_t nrows, int64_t nnz, int32_t *__restrict__ rows)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnz)
-        return;
-    // first r in [0, nrows] with rp[r] >= i+1, minus one
-    rows[i] = (int32_t)(lower_bound_rp(rp, 0, (int64_t)nrows + 1, i + 1) - 1);
+    constexpr int PER = EXP_TILE / 256;
+    __shared__ int s_mark[EXP_TILE];
+    __shared__ int s_wmax[8];
+    __shared__ int64_t s_r[2];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t tbase = (int64_t)blockIdx.x * EXP_TILE;
+    const int cnt = (int)min((int64_t)EXP_TILE, nnz - tbase);
+    for (int j = tid; j < EXP_TILE; j += 256)
+        s_mark[j] = -1;
+    if (tid < 2) {
+        const int64_t pos = tid == 0 ? tbase : tbase + cnt - 1;
+        s_r[tid] = lower_bound_rp(rp, 0, (int64_t)nrows + 1, pos + 1) - 1;
+    }
+    __syncthreads();
+    const int64_t r0 = s_r[0], r1 = s_r[1];
+    if (tid == 0)
+        s_mark[0] = (int)r0;
+    for (int64_t r = r0 + 1 + tid; r <= r1; r += 256)
+        atomicMax(&s_mark[(int)((int64_t)rp[r] - tbase)], (int)r);  // in (0, cnt-1] by the choice of r0, r1
+    __syncthreads();
+    // running maximum: PER consecutive marks per thread, then across the threads
+    int v[PER];
+    int run = -1;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        run = max(run, s_mark[tid * PER + k]);
+        v[k] = run;
+    }
+    int inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d)
+            inc = max(inc, o);
+    }
+    if (lane == 31)
+        s_wmax[w] = inc;
+    __syncthreads();
+    int before = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0)
+        before = -1;
+    for (int k = 0; k < w; k++)
+        before = max(before, s_wmax[k]);
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        s_mark[tid * PER + k] = max(v[k], before);
+    __syncthreads();
+    for (int j = tid; j < cnt; j += 256)
+        rows[tbase + j] = s_mark[j];
 }
 
-template <typename CT>
-__global__ void k_col_count(const int32_t *__restrict__ ci, int64_t nnz, CT *__restrict__ cnt)
+// Output rowptrs from the column-sorted keys: rp[c] = first position whose key is >= c.
+// Position i writes rp for every column in (keys[i-1], keys[i]] -- each column exactly once.
+// Position nnz closes the tail with keys[nnz] := ncols.  Four positions per thread (one 16-byte
+// load; the workspace hands out 256-byte aligned blocks).
+template <typename RPT>
+__global__ void k_key_bounds(const int32_t *__restrict__ keys, int64_t nnz, int32_t ncols, RPT *__restrict__ rp)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nnz)
-        atomicAdd(&cnt[ci[i]], (CT)1);
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 > nnz)
+        return;
+    int32_t k[5];
+    k[0] = i0 ? keys[i0 - 1] : -1;
+    if (i0 + 4 <= nnz) {
+        const int4 q = *reinterpret_cast<const int4 *>(keys + i0);
+        k[1] = q.x, k[2] = q.y, k[3] = q.z, k[4] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            k[j + 1] = i0 + j < nnz ? keys[i0 + j] : ncols;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (i0 + j > nnz)
+            break;
+        for (int32_t c = k[j] + 1; c <= k[j + 1]; c++)
+            rp[c] = (RPT)(i0 + j);
+    }
 }
 
 __global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ out, int64_t n)
@@ -82,33 +153,32 @@ static int transpose_core(int32_t nrows, int32_t ncols, int64_t nnz, const RPT *
                           CoreOut &out, cudaStream_t s)
 {
     constexpr bool HASV = !std::is_same<VT, NoPayload>::value;
-    using CT = typename std::conditional<sizeof(RPT) == 8, unsigned long long, int>::type;
     CSRK_TRACE_MARK("transpose: enter", s);
-    // 1. column counts -> output rowptrs
-    DevBuf cnt;
-    CSRK_TRY(cnt.alloc_zero(sizeof(RPT) * ((size_t)ncols + 1), s));
     CSRK_TRY(out.rp.alloc_owned(sizeof(RPT) * ((size_t)ncols + 1), s));
-    if (nnz)
-        CSRK_LAUNCH((k_col_count<CT>), (unsigned)div_up(nnz, 256), 256, 0, s, ci, nnz, cnt.as<CT>());
-    CSRK_TRY((exclusive_scan<RPT>(ArrayLoader<RPT>{cnt.as<RPT>()}, (int64_t)ncols, out.rp.as<RPT>(), s)));
-    cnt.reset();
     CSRK_TRY(out.ci.alloc_owned(sizeof(int32_t) * (size_t)nnz, s));
     if (HASV)
         CSRK_TRY(out.vs.alloc_owned(sizeof(VT) * (size_t)nnz, s));
-    if (nnz == 0)
+    if (nnz == 0) {
+        CSRK_CUDA(cudaMemsetAsync(out.rp.p, 0, sizeof(RPT) * ((size_t)ncols + 1), s));
         return CSRK_OK;
-    CSRK_TRACE_MARK("transpose: counts+scan+alloc", s);
+    }
 
-    // 2. source row of every entry
+    // 1. source row of every entry
     DevBuf rows0;
     CSRK_TRY(rows0.alloc(sizeof(int32_t) * (size_t)nnz, s));
-    CSRK_LAUNCH((k_expand_rows<RPT>), (unsigned)div_up(nnz, 256), 256, 0, s, rp, nrows, nnz, rows0.as<int32_t>());
+    CSRK_LAUNCH((k_expand_rows<RPT>), (unsigned)div_up(nnz, EXP_TILE), 256, 0, s, rp, nrows, nnz, rows0.as<int32_t>());
 
     CSRK_TRACE_MARK("transpose: expand rows", s);
-    // 3. stable LSD radix sort by column; the payloads land in out.ci / out.vs
+    // 2. stable LSD radix sort by column; the payloads land in out.ci / out.vs
+    DevBuf skeys;
+    CSRK_TRY(skeys.alloc(sizeof(int32_t) * (size_t)nnz, s));
     CSRK_TRY((radix_sort_by_key<VT>(ci, rows0.as<int32_t>(), vs, nnz, key_bits(ncols), out.ci.as<int32_t>(),
-                                    HASV ? out.vs.as<VT>() : nullptr, s)));
+                                    HASV ? out.vs.as<VT>() : nullptr, s, skeys.as<int32_t>())));
     CSRK_TRACE_MARK("transpose: radix sort", s);
+    // 3. output rowptrs = where each column starts in the sorted keys
+    CSRK_LAUNCH((k_key_bounds<RPT>), (unsigned)div_up(div_up(nnz + 1, 4), 256), 256, 0, s, skeys.as<int32_t>(), nnz, ncols,
+                out.rp.as<RPT>());
+    CSRK_TRACE_MARK("transpose: rowptrs", s);
     return CSRK_OK;
 }
 

@@ -62,7 +62,10 @@ int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *
 int64_t csrk_launch_count(void);
 int csrk_synchronize(void);
 /* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 panel/slab kernel;
- * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan. */
+ * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan;
+ * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
+ * "radix_bits"  0 | 8 | 9 digit width of the stable sort behind transpose/order_columns
+ *               (0 picks 9 when that saves a pass). */
 int csrk_set_option(const char *name, int64_t value);
 /* the library's own (non-blocking) stream, as a cudaStream_t */
 int csrk_get_stream(void **stream);
