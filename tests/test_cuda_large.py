@@ -93,6 +93,38 @@ def test_transpose_large(kernel, shape, nnz, dtype):
     assert np.array_equal(TT.values, A.values.astype(np.float64))
 
 
+@pytest.mark.parametrize("bits", [8, 9])
+@pytest.mark.parametrize("shape,nnz", [((700, 200), 4096 * 3), ((300, 400), 4096 * 2 + 3), ((900, 70000), 50001),
+                                       ((64, 300000), 33000), ((5, 9), 17)])
+def test_transpose_digit_widths_and_stability(kernel, bits, shape, nnz):
+    """Both digit widths of the stable sort (1-3 passes, full and ragged last tiles) on rows with
+    unsorted, duplicated columns: equal columns must keep their input order (structure.py:168-182)."""
+    rng = np.random.default_rng(nnz + bits)
+    nr, nc = shape
+    lens = rng.multinomial(nnz, np.ones(nr) / nr)
+    rp = np.zeros(nr + 1, np.int32)
+    np.cumsum(lens, out=rp[1:])
+    ci = rng.integers(0, nc, nnz).astype(np.int32)
+    ci[rng.random(nnz) < 0.3] = nc // 3  # one hot column with many duplicates inside rows
+    A = CSR(nr, nc, nnz, rp, ci, rng.standard_normal(nnz))
+    kernel.set_option("radix_bits", bits)
+    h = kernel.to_handle(A)
+    try:
+        th = kernel.transpose(h)
+        T = kernel.from_handle(th)
+        sh = kernel.transpose(h, False)
+        S = kernel.from_handle(sh)
+        kernel.release_handle(th)
+        kernel.release_handle(sh)
+    finally:
+        kernel.release_handle(h)
+        kernel.set_option("radix_bits", 0)
+    R = orc.transpose(A)
+    assert np.array_equal(T.rowptrs, R.rowptrs) and np.array_equal(T.colinds, R.colinds)
+    assert np.array_equal(T.values, R.values)
+    assert S.values is None and np.array_equal(S.rowptrs, R.rowptrs) and np.array_equal(S.colinds, R.colinds)
+
+
 def test_order_columns_large_and_idempotent(kernel):
     rng = np.random.default_rng(8)
     A = synth.powerlaw_csr(3000, 50000, 200000, seed=42, dtype="f4", alpha=1.0)
