@@ -174,7 +174,15 @@ def run_ours(args):
     x_host = np.random.default_rng(77).standard_normal(A.ncols).astype(np.float32)
     row_counts = [A.nrows] * world
     t0 = time.perf_counter()
-    ds = DistSpMV(A, row_counts, x_dtype="f4", kernel=K, fused=args.fused, chunks=args.chunks if world > 1 else 1)
+    want_nvls = world > 1 and args.nvls != "off" and not args.fused and args.chunks == 1
+    if args.nvls == "on" and not want_nvls:
+        raise SystemExit("--nvls on needs --gpus > 1 and neither --fused nor --chunks > 1")
+    ds = DistSpMV(A, row_counts, x_dtype="f4", kernel=K, fused=args.fused, chunks=args.chunks if world > 1 else 1,
+                  nvls=want_nvls)
+    if want_nvls and ds.nvls is None and args.nvls == "on":
+        raise SystemExit(f"--nvls on: multicast path unavailable ({getattr(ds, 'nvls_error', '?')})")
+    if want_nvls and ds.nvls is None:
+        log(f"[rank {rank}] NVLS path unavailable ({getattr(ds, 'nvls_error', '?')}); using the NCCL collectives")
     t_handle = time.perf_counter() - t0
     ds.set_x(x_host)
     log(f"[rank {rank}] block {A}  gen {t_gen:.1f}s  to_handle {t_handle:.2f}s")
@@ -233,7 +241,31 @@ def run_ours(args):
 
     # ---- N>1: what the two collectives cost on their own (same buffers, same stream)
     coll = None
-    if world > 1 and ds.symm is None:
+    if world > 1 and ds.nvls is not None:
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return allmax(a.elapsed_time(b) / steps)
+        st = torch.cuda.current_stream().cuda_stream
+        nb = int(ds.x.numel() * ds.x.element_size())
+
+        def bcast():
+            if rank == 0:
+                K.mc_broadcast(ds.x_mc, ds.x.data_ptr(), nb, st)
+            ds.nvls[1].barrier()
+        t_b = timed(bcast)
+        t_bar = timed(lambda: ds.nvls[0].barrier())
+        coll = {"multicast_broadcast_x_plus_barrier_ms": round(t_b, 5), "broadcast_x_bytes": nb,
+                "barrier_ms": round(t_bar, 5), "gather_y": "inside the SpMV kernel (multimem.st per finished row)",
+                "note": "NVLink multicast through the NVSwitch (symmetric memory), timed alone"}
+    elif world > 1 and ds.symm is None:
         def timed(fn):
             for _ in range(3):
                 fn()
@@ -273,6 +305,15 @@ def run_ours(args):
     y_all = ds.result()
     y_dev = y_all[rank * A.nrows:(rank + 1) * A.nrows]
     assert np.allclose(y_dev, yn, rtol=1e-9, atol=1e-9), "device-resident and host-API results differ"
+    if world > 1:
+        # every OTHER rank's rows must have arrived here too: compare per-segment checksums
+        mine = torch.tensor([float(np.sum(yn)), float(np.abs(yn).sum())], dtype=torch.float64, device="cuda")
+        sums = torch.zeros(2 * world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(sums, mine)
+        sums = sums.cpu().numpy().reshape(world, 2)
+        for r in range(world):
+            seg = y_all[r * A.nrows:(r + 1) * A.nrows]
+            assert abs(float(np.sum(seg)) - sums[r, 0]) <= 1e-9 * sums[r, 1] + 1e-300, f"rank {r}'s rows did not arrive intact"
     if h_e2e is not ds.handle:
         K.release_handle(h_e2e)
 
@@ -286,7 +327,10 @@ def run_ours(args):
             "global_shape": [A.nrows * world, A.ncols], "global_nnz": A.nnz * world,
             "row_lengths": "rank-size power law alpha=1.0, mean 100, cap ncols, random row order",
             "columns": "stratified uniform" if args.col_skew == 1.0 else f"stratified, skew t^{args.col_skew}",
-            "parallelism": f"row-partitioned x{world}; step = NCCL broadcast(x) + " + (
+            "parallelism": (f"row-partitioned x{world}; step = barrier + NVLS multicast copy of x (root) + barrier + SpMV "
+                            "kernel storing each finished y row once through the NVLink multicast address (fused "
+                            "gather) + barrier") if ds.nvls is not None else
+                           f"row-partitioned x{world}; step = NCCL broadcast(x) + " + (
                 "SpMV kernel storing y rows into every rank's buffer over NVLink (fused gather) + barrier"
                 if ds.symm is not None else
                 f"local SpMV + NCCL all-gather(y) in {ds.chunks} row chunks, each gather overlapping the next chunk's SpMV"),
@@ -500,6 +544,8 @@ def main():
     ap.add_argument("--col-skew", type=float, default=1.0)
     ap.add_argument("--spgemm-scale", type=float, default=1.0, help="scale of configs[2] for the A*A^T leg (0 = skip)")
     ap.add_argument("--chunks", type=int, default=1, help="N>1: row chunks whose all-gathers overlap the next chunk's SpMV")
+    ap.add_argument("--nvls", choices=["auto", "on", "off"], default="auto",
+                    help="N>1: NVLink-multicast broadcast + in-kernel multicast gather (default when the box supports it)")
     ap.add_argument("--fused", action="store_true", help="fused SpMV+gather over peer memory instead of the NCCL all-gather")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the SpMV kernel, if known")
     args = ap.parse_args()

@@ -41,6 +41,8 @@ SIGNATURES = {
     "csrk_spmv": (_int, [_vp, _vp, _int, _vp]),
     "csrk_spmv_dev": (_int, [_vp, _vp, _int, _vp, _vp]),
     "csrk_spmv_dev_multi": (_int, [_vp, _vp, _int, _P(_vp), _int, _vp]),
+    "csrk_spmv_dev_mc": (_int, [_vp, _vp, _int, _vp, _vp, _vp]),
+    "csrk_mc_broadcast": (_int, [_vp, _vp, _i64, _vp]),
     "csrk_spgemm": (_int, [_vp, _vp, _P(_vp)]),
     "csrk_spgemm_abt": (_int, [_vp, _vp, _P(_vp)]),
     "csrk_spgemm_stats": (_int, [_vp, _P(_i64), _P(_i64)]),

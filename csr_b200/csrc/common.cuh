@@ -173,7 +173,9 @@ int psf3_run(csrk_matrix *h, Psf3Plan *p, const void *d_x, double *d_y, cudaStre
 
 // ops implemented across the .cu files (all enqueue on `s`, no sync unless stated)
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s);
-int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d_ys, int n_out, cudaStream_t s);
+int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d_ys, int n_out, cudaStream_t s,
+                   bool multicast = false);
+int mc_broadcast_run(void *mc_dst, const void *src, int64_t nbytes, cudaStream_t s);
 int transpose_run(csrk_matrix *a, int with_values, csrk_matrix **out, cudaStream_t s);  // syncs internally
 int order_columns_run(csrk_matrix *h, cudaStream_t s);                                  // syncs internally
 int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s);        // syncs internally

@@ -572,6 +572,27 @@ int csrk_spmv_dev_multi(csrk_h h, const void *d_x, int x_kind, double *const *d_
     return spmv_run_multi(h, d_x, x_kind, d_ys, n_out, (cudaStream_t)stream);
 }
 
+int csrk_spmv_dev_mc(csrk_h h, const void *d_x, int x_kind, double *d_y, double *d_y_mc, void *stream)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_ARG(x_kind == 4 || x_kind == 8, "x_kind must be 4 or 8 (got %d)", x_kind);
+    CSRK_ARG(h->nrows == 0 || (d_y != nullptr && d_y_mc != nullptr), "y / multicast y is NULL");
+    CSRK_ARG(((uintptr_t)d_y_mc & 7) == 0, "multicast y must be 8-byte aligned");
+    CSRK_ARG(h->ncols == 0 || d_x != nullptr, "x is NULL");
+    CSRK_TRY(ensure_init());
+    double *ys[2] = {d_y, d_y_mc};
+    return spmv_run_multi(h, d_x, x_kind, ys, 2, (cudaStream_t)stream, true);
+}
+
+int csrk_mc_broadcast(void *mc_dst, const void *d_src, int64_t nbytes, void *stream)
+{
+    CSRK_ARG(nbytes >= 0 && nbytes % 4 == 0, "nbytes must be a non-negative multiple of 4 (got %lld)", (long long)nbytes);
+    CSRK_ARG(nbytes == 0 || (mc_dst != nullptr && d_src != nullptr), "NULL pointer");
+    CSRK_ARG((((uintptr_t)mc_dst | (uintptr_t)d_src) & 15) == 0, "multicast copies need 16-byte aligned pointers");
+    CSRK_TRY(ensure_init());
+    return mc_broadcast_run(mc_dst, d_src, nbytes, (cudaStream_t)stream);
+}
+
 int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y)
 {
     CSRK_ARG(h != nullptr, "NULL handle");

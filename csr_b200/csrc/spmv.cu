@@ -55,10 +55,19 @@ constexpr int SPMV_MAX_OUT = 8;
 struct YOut {
     double *p[SPMV_MAX_OUT];
     int n;
+    int mc;  // p[1] is an NVLink multicast (NVLS) address: ONE store lands in every GPU of the group
 };
-__device__ __forceinline__ void store_y(const YOut &y, int64_t r, double v)
+// `final` = the value is the row's result (not the head piece of a row that continues in later
+// tiles and gets its carries added by k_spmv_fixup): only final values leave the GPU.
+__device__ __forceinline__ void store_y(const YOut &y, int64_t r, double v, bool final)
 {
     y.p[0][r] = v;
+    if (!final)
+        return;
+    if (y.mc) {
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(y.p[1] + r), "d"(v) : "memory");
+        return;
+    }
 #pragma unroll
     for (int k = 1; k < SPMV_MAX_OUT; k++)
         if (k < y.n)
@@ -176,7 +185,8 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
     // scalar-per-row for short rows; long rows are queued for the warps
     for (int32_t r = rlo + tid; r < rhi; r += SPMV_BLOCK) {
         const int s0 = (int)((int64_t)rp[r] - base);
-        const int e0 = (int)(min((int64_t)rp[r + 1], tend) - base);
+        const int64_t re = (int64_t)rp[r + 1];
+        const int e0 = (int)(min(re, tend) - base);
         if (e0 - s0 > SPMV_LONG) {
             int slot = atomicAdd(&q_n, 1);
             q_row[slot] = r;
@@ -184,7 +194,7 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
             double s = 0.0;
             for (int i = s0; i < e0; i++)
                 s += (double)prod[i];
-            store_y(y, r, s);  // complete row, or the head piece of a row that continues (carries are added later)
+            store_y(y, r, s, re <= tend);  // complete row, or the head piece of a row that continues (carries are added later)
         }
     }
     __syncthreads();
@@ -192,13 +202,14 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
     for (int q = tid >> 5; q < nq; q += SPMV_BLOCK / 32) {
         const int32_t r = q_row[q];
         const int s0 = (int)((int64_t)rp[r] - base);
-        const int e0 = (int)(min((int64_t)rp[r + 1], tend) - base);
+        const int64_t re = (int64_t)rp[r + 1];
+        const int e0 = (int)(min(re, tend) - base);
         double s = 0.0;
         for (int i = s0 + (tid & 31); i < e0; i += 32)
             s += (double)prod[i];
         s = warp_sum(s);
         if ((tid & 31) == 0)
-            store_y(y, r, s);
+            store_y(y, r, s, re <= tend);
     }
 }
 
@@ -224,7 +235,7 @@ __global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict_
     double tot = 0.0;
     for (int64_t u = t; u <= tlast; u++)
         tot += carry[u];
-    store_y(y, row, y.p[0][row] + tot);
+    store_y(y, row, y.p[0][row] + tot, true);
 }
 
 static int ensure_plan(csrk_matrix *h, cudaStream_t s, SpmvPlan **out)
@@ -348,15 +359,18 @@ static int ensure_psf(csrk_matrix *h, int x_kind, PsfPlan **out)
     return CSRK_OK;
 }
 
-int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d_ys, int n_out, cudaStream_t s)
+int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d_ys, int n_out, cudaStream_t s,
+                   bool multicast)
 {
     YOut yo;
     yo.n = n_out;
+    yo.mc = multicast ? 1 : 0;
     for (int k = 0; k < SPMV_MAX_OUT; k++)
         yo.p[k] = k < n_out ? d_ys[k] : nullptr;
     if (h->nrows == 0)
         return CSRK_OK;
     if (h->nnz == 0) {
+        // (a multicast address takes plain stores too: multimem.st is an ordinary STG in SASS)
         for (int k = 0; k < n_out; k++)
             CSRK_LAUNCH(k_zero_f64, (unsigned)div_up(h->nrows, 256), 256, 0, s, d_ys[k], (int64_t)h->nrows);
         return CSRK_OK;
@@ -388,7 +402,37 @@ int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s)
 {
     double *ys[1] = {d_y};
-    return spmv_run_multi(h, d_x, x_kind, ys, 1, s);
+    return spmv_run_multi(h, d_x, x_kind, ys, 1, s, false);
+}
+
+// ---- NVLS broadcast: copy `nbytes` from local memory to a multicast address -----------------
+// (the x broadcast of the row-partitioned SpMV: the root stores once, the NVSwitch replicates)
+// Measured (tools/exp_mc.py, 32 MB): 60 us = 530 GB/s at 2 GPUs, 84 us at 8 -- the same for weak or
+// relaxed.sys stores, 1x/4x/8x unrolling and for the copy engine (cudaMemcpyAsync to the multicast
+// address, 75 us): the multicast write rate of the fabric, not this kernel, sets it.
+__global__ void __launch_bounds__(256) k_mc_copy(float *__restrict__ mc_dst, const float *__restrict__ src, int64_t n16,
+                                                 int64_t nwords)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < n16; i += stride) {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(src) + i);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + 4 * i), "f"(q.x),
+                     "f"(q.y), "f"(q.z), "f"(q.w)
+                     : "memory");
+    }
+    for (int64_t i = 4 * n16 + i0; i < nwords; i += stride)  // tail: < 4 words
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_dst + i), "f"(src[i]) : "memory");
+}
+
+int mc_broadcast_run(void *mc_dst, const void *src, int64_t nbytes, cudaStream_t s)
+{
+    if (nbytes == 0)
+        return CSRK_OK;
+    const int64_t nwords = nbytes / 4, n16 = nbytes / 16;
+    const unsigned grid = (unsigned)std::min<int64_t>(div_up(std::max<int64_t>(n16, 1), 256), (int64_t)ctx().sm_count * 8);
+    CSRK_LAUNCH(k_mc_copy, grid, 256, 0, s, (float *)mc_dst, (const float *)src, n16, nwords);
+    return CSRK_OK;
 }
 
 }  // namespace csrk

@@ -68,10 +68,20 @@ class DistSpMV:
     c+1.  Every rank must use the same ``chunks``.  Measured on 8 B200 (1M x 8M block per GPU):
     0.878 ms/step with 1 chunk, 0.923 with 4, 1.068 with 8 -- the smaller kernels pay wave
     tails and share SMs with NCCL -- so the default is 1.
+
+    ``nvls=True`` replaces both NCCL collectives by NVLink multicast through the NVSwitch
+    (symmetric memory + ``multicast_ptr``): the root copies x ONCE to the multicast address of a
+    symmetric x buffer (``csrk_mc_broadcast``), and the SpMV kernel stores every finished row once
+    through the multicast address of its y segment (``csrk_spmv_dev_mc``) -- compute and gather are
+    one kernel, and no GPU sends the same bytes world-1 times.  Two symmetric-memory barriers
+    order a step (x landed / everyone entered, y landed).  This is the default on GPUs; it falls back
+    to the NCCL collectives (``nvls_error`` says why) when the box has no multicast support, and
+    ``fused=True`` or ``chunks>1`` select the other variants.  Measured, 1M x 8M block per GPU on 8 B200:
+    0.579 ms/step against 0.880 with NCCL broadcast + all-gather (0.4265 vs 0.468 on 2).
     """
 
     def __init__(self, local, row_counts, *, x_dtype="f4", device=None, group=None, compute=None, kernel=None,
-                 fused=False, chunks=1):
+                 fused=False, chunks=1, nvls=True):
         import torch
         self.torch = torch
         self.group = group
@@ -103,6 +113,11 @@ class DistSpMV:
         self.peer_ptrs = None
         if fused and compute is None and self.world > 1 and self.world <= 8 and self.device.type == "cuda":
             self._setup_fused(group)
+        self.nvls = None          # (y handle, x handle) when the multicast path is active
+        self.x_in = self.x        # what the kernels read (the symmetric x buffer under nvls)
+        if (nvls and compute is None and self.world > 1 and self.device.type == "cuda" and self.symm is None
+                and not fused and self.chunks == 1):
+            self._setup_nvls(group)
         if self.ybuf is None:
             self.ybuf = torch.zeros(max(self.coff[-1], 1), dtype=torch.float64, device=self.device)
         self.handles = []
@@ -155,6 +170,29 @@ class DistSpMV:
             self.ybuf, self.symm, self.peer_ptrs = None, None, None
             self.fused_error = repr(e)
 
+    def _setup_nvls(self, group):
+        torch = self.torch
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            dist = _dist()
+            g = group if group is not None else dist.group.WORLD
+            ybuf = symm_mem.empty(max(self.coff[-1], 1), dtype=torch.float64, device=self.device)
+            hy = symm_mem.rendezvous(ybuf, g)
+            xbuf = symm_mem.empty(max(self.ncols, 4), dtype=self.x.dtype, device=self.device)
+            hx = symm_mem.rendezvous(xbuf, g)
+            if not getattr(hy, "multicast_ptr", 0) or not getattr(hx, "multicast_ptr", 0):
+                raise RuntimeError("symmetric memory has no multicast support on this box")
+            ybuf.zero_()
+            xbuf.zero_()
+            self.ybuf, self.x_in, self.nvls = ybuf, xbuf, (hy, hx)
+            self.y_mc = int(hy.multicast_ptr) + self.rank * self.cpad[0] * 8
+            self.x_mc = int(hx.multicast_ptr)
+            torch.cuda.synchronize()
+            hy.barrier()
+        except Exception as e:  # keep the NCCL collectives
+            self.ybuf, self.x_in, self.nvls = None, self.x, None
+            self.nvls_error = repr(e)
+
     def _seg(self, c, r=None):
         "This rank's (or rank r's) segment of chunk c inside the gather buffer (padded length)."
         r = self.rank if r is None else r
@@ -163,6 +201,7 @@ class DistSpMV:
 
     def _cuda_compute(self, x, y, c=0):
         stream = self.torch.cuda.current_stream().cuda_stream
+        x = self.x_in
         self.kernel.mult_vec_dev(self.handles[c], x.data_ptr(), x.element_size(), y.data_ptr(), stream)
 
     def set_x(self, x_host):
@@ -187,6 +226,23 @@ class DistSpMV:
         """One distributed SpMV; the gather buffer then holds every rank's rows
         (``result()`` strips the padding)."""
         dist = _dist()
+        if self.nvls is not None:
+            hy, hx = self.nvls
+            stream = self.torch.cuda.current_stream().cuda_stream
+            # No rank may store rows into a peer's buffer while that peer still reads the previous
+            # result: the first barrier of a step is only passed once every rank has entered the step
+            # (stream order puts its readers before that).  The x barrier doubles as that barrier.
+            if broadcast_x:
+                if self.rank == 0:
+                    self.kernel.mc_broadcast(self.x_mc, self.x.data_ptr(), self.x.numel() * self.x.element_size(), stream)
+                hx.barrier()          # x has landed everywhere
+            else:
+                hy.barrier()
+            seg = self._seg(0)
+            self.kernel.mult_vec_dev_mc(self.handle, self.x_in.data_ptr(), self.x_in.element_size(), seg.data_ptr(),
+                                        self.y_mc, stream)
+            hy.barrier()              # all ranks' rows have landed everywhere
+            return self.ybuf
         if self.world > 1 and broadcast_x:
             dist.broadcast(self.x, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
         if self.symm is not None:

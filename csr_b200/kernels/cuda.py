@@ -234,6 +234,19 @@ def mult_vec_dev_multi(h: cuda_h, x_ptr: int, x_itemsize: int, y_ptrs, stream: i
                                         C.c_void_p(stream)), "mult_vec_dev_multi")
 
 
+def mult_vec_dev_mc(h: cuda_h, x_ptr: int, x_itemsize: int, y_ptr: int, y_mc_ptr: int, stream: int = 0) -> None:
+    """SpMV whose finished rows are also stored through the NVLink multicast address ``y_mc_ptr``
+    (this rank's segment of a symmetric gather buffer): one store reaches every GPU."""
+    N.check(N.lib().csrk_spmv_dev_mc(_live(h), C.c_void_p(x_ptr), int(x_itemsize), C.c_void_p(y_ptr),
+                                     C.c_void_p(y_mc_ptr), C.c_void_p(stream)), "mult_vec_dev_mc")
+
+
+def mc_broadcast(mc_dst_ptr: int, src_ptr: int, nbytes: int, stream: int = 0) -> None:
+    "Copy local device memory to an NVLink multicast address (the root's side of the x broadcast)."
+    N.check(N.lib().csrk_mc_broadcast(C.c_void_p(mc_dst_ptr), C.c_void_p(src_ptr), int(nbytes),
+                                      C.c_void_p(stream)), "mc_broadcast")
+
+
 def from_device_arrays(nrows, ncols, nnz, rowptrs_ptr, rp_is64, colinds_ptr, values_ptr, val_kind,
                        stream: int = 0, csr_cls=None) -> cuda_h:
     """Build a handle from device arrays (D2D copy)."""

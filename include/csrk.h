@@ -106,6 +106,15 @@ int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stre
  * d_ys[0] (this GPU) AND to d_ys[1..n_out) (the same y segment inside the peers' gather buffers,
  * NVLink peer / symmetric memory), n_out <= 8.  d_ys is a HOST array of device pointers. */
 int csrk_spmv_dev_multi(csrk_h h, const void *d_x, int x_kind, double *const *d_ys, int n_out, void *stream);
+/* The same over NVLink multicast (NVLS): d_y_mc is the MULTICAST address of this rank's y segment
+ * inside a symmetric gather buffer (cuMulticast* / torch symmetric memory `multicast_ptr` + offset),
+ * d_y the segment's ordinary local address.  Every finished row is stored once with multimem.st and
+ * the NVSwitch replicates it into every GPU of the group; the caller adds the barrier. */
+int csrk_spmv_dev_mc(csrk_h h, const void *d_x, int x_kind, double *d_y, double *d_y_mc, void *stream);
+/* NVLS broadcast: copy nbytes (multiple of 4, 16-byte aligned pointers) from local device memory to a
+ * multicast address -- the root's half of "x is broadcast" (BASELINE north_star), one NVLink egress
+ * instead of world-1.  The caller orders it with barriers on both sides. */
+int csrk_mc_broadcast(void *mc_dst, const void *d_src, int64_t nbytes, void *stream);
 
 /* ---- mult_ab / mult_abt: multiply.py:13-57; lk_mkl_spmab/spmabt ----------
  * C = A*B (a.ncols == b.nrows) and C = A*B^T (a.ncols == b.ncols) as a NEW

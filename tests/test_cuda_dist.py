@@ -1,7 +1,7 @@
 """
 GPU (needs >= 2 GPUs on the box; skipped otherwise): the row-partitioned SpMV over NCCL with the
-FUSED SpMV + gather kernel (rows stored straight into every rank's symmetric-memory buffer) against
-the NCCL all-gather path and the oracle.
+FUSED SpMV + gather kernel (rows stored straight into every rank's symmetric-memory buffer) and the
+NVLink-multicast (NVLS) path against the NCCL all-gather path and the oracle.
 """
 
 import os
@@ -34,7 +34,7 @@ def _worker(rank, world, port, q):
         ref = orc.mult_vec(A, x)
         out = {}
         for fused in (True, False):  # fused is opt-in; the default is the NCCL all-gather
-            ds = DistSpMV(mine, counts, x_dtype="f4", fused=fused)
+            ds = DistSpMV(mine, counts, x_dtype="f4", fused=fused, nvls=False)
             if rank == 0:
                 ds.set_x(x)
             for _ in range(3):
@@ -55,9 +55,27 @@ def _worker(rank, world, port, q):
         dist.barrier()
         yc = ds.result()
         ds.close()
+        # NVLink multicast: x copied once to the multicast address, rows stored once by the SpMV kernel
+        ds = DistSpMV(mine, counts, x_dtype="f4")  # the default
+        if rank == 0:
+            ds.set_x(x)
+        for _ in range(3):
+            ds.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ym, was_nvls = ds.result(), ds.nvls is not None
+        # a second x through the same buffers (stale data would show)
+        if rank == 0:
+            ds.set_x(2.0 * x)
+        ds.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ym2 = ds.result()
+        ds.close()
         tol = dict(rtol=1e-5, atol=1e-5 * np.abs(ref).max())
-        ok = bool(np.allclose(yf, ref, **tol) and np.array_equal(yf, yn) and np.allclose(yc, ref, **tol))
-        q.put((rank, ok, was_fused))
+        ok = bool(np.allclose(yf, ref, **tol) and np.array_equal(yf, yn) and np.allclose(yc, ref, **tol)
+                  and np.array_equal(ym, yn) and np.array_equal(ym2, 2.0 * yn))
+        q.put((rank, ok, (was_fused, was_nvls)))
     finally:
         dist.destroy_process_group()
 
@@ -76,6 +94,7 @@ def test_fused_gather_two_gpus():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, ok, was_fused in res:
-        assert ok, f"rank {rank}: fused gather differs from the NCCL path / the oracle"
-    assert all(r[2] for r in res), "symmetric memory was not available: the fused path did not run"
+    for rank, ok, ran in res:
+        assert ok, f"rank {rank}: fused / multicast gather differs from the NCCL path / the oracle"
+    assert all(r[2][0] for r in res), "symmetric memory was not available: the fused path did not run"
+    assert all(r[2][1] for r in res), "NVLink multicast was not available: the NVLS path did not run"
