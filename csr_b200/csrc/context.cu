@@ -380,6 +380,8 @@ int csrk_set_option(const char *name, int64_t value)
     } else if (!strcmp(name, "radix_bits")) {
         CSRK_ARG(value == 0 || value == 8 || value == 9, "radix_bits must be 0, 8 or 9");
         options().radix_bits = value;
+    } else if (!strcmp(name, "own_chunk_prod")) {
+        options().own_chunk_prod = value;
     } else if (!strcmp(name, "own_nw")) {
         CSRK_ARG(value == 8 || value == 16, "own_nw must be 8 or 16");
         options().own_nw = value;

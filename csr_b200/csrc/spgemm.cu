@@ -75,8 +75,10 @@ __global__ void __launch_bounds__(256) k_row_products(MatView A, MatView B, int6
         p = warp_sum(p);
         if (lane == 0) {
             prod[row] = p;
-            if (p)
+            if (p) {
                 atomicAdd(total, (unsigned long long)p);
+                atomicMax(total + 1, (unsigned long long)p);  // the heaviest row decides whether rows get chunked
+            }
         }
     }
 }
@@ -208,10 +210,11 @@ template <bool SMEM_BM, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin,
                                                         int32_t *__restrict__ row_nnz, unsigned *__restrict__ gbm,
                                                         int n_words, int *__restrict__ work_counter,
-                                                        unsigned *__restrict__ keep, int32_t *__restrict__ keep_slot)
+                                                        unsigned *__restrict__ keep, int32_t *__restrict__ keep_slot,
+                                                        const int *__restrict__ item_off)
 {
     extern __shared__ unsigned s_bm[];
-    __shared__ int s_idx, s_count;
+    __shared__ int s_idx, s_item, s_count;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     unsigned *bm = SMEM_BM ? s_bm : gbm + (size_t)blockIdx.x * n_words;
     if (SMEM_BM) {
@@ -221,15 +224,43 @@ __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, co
     while (true) {
         __syncthreads();
         if (tid == 0) {
-            s_idx = atomicAdd(work_counter, 1);
+            // item_off (optional): heavy rows are cut into chunks of A entries, one work item each
+            const int item = atomicAdd(work_counter, 1);
+            int ri = item < nbin ? item : -1;
+            if (item_off) {
+                ri = -1;
+                if (item < item_off[nbin]) {
+                    int lo = 0, hi = nbin;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (item_off[mid] <= item)
+                            lo = mid;
+                        else
+                            hi = mid;
+                    }
+                    ri = lo;
+                }
+            }
+            s_idx = ri;
+            s_item = item;
             s_count = 0;
         }
         __syncthreads();
         const int idx = s_idx;
-        if (idx >= nbin)
+        if (idx < 0)
             break;
         const int32_t row = rows[idx];
-        const int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+        int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+        int nch = 1;
+        if (item_off) {
+            nch = item_off[idx + 1] - item_off[idx];
+            if (nch > 1) {
+                const int chunk = s_item - item_off[idx];
+                const int64_t len = ae - as;
+                ae = as + len * (chunk + 1) / nch;
+                as = as + len * chunk / nch;
+            }
+        }
         for (int64_t jj = as + w; jj < ae; jj += THREADS / 32) {
             const int32_t j = A.ci[jj];
             const int64_t bs = ld_rp(B.rp, B.rp64, j), be = ld_rp(B.rp, B.rp64, (int64_t)j + 1);
@@ -241,6 +272,20 @@ __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, co
         __syncthreads();
         int count = 0;
         unsigned *dst = keep ? keep + (size_t)idx * n_words : nullptr;
+        if (nch > 1) {
+            // OR this chunk's columns into the row's (zero-initialised) kept bitmap; k_sym_finish counts it
+            for (int i = tid; i < n_words; i += THREADS) {
+                const unsigned bits = SMEM_BM ? bm[i] : __ldcg(&bm[i]);
+                if (bits) {
+                    atomicOr(&dst[i], bits);
+                    if (SMEM_BM)
+                        bm[i] = 0;
+                    else
+                        __stcg(&bm[i], 0u);
+                }
+            }
+            continue;
+        }
         for (int i = tid; i < n_words; i += THREADS) {
             const unsigned bits = SMEM_BM ? bm[i] : __ldcg(&bm[i]);
             if (dst)
@@ -262,6 +307,32 @@ __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, co
             if (keep_slot)
                 keep_slot[row] = idx;
         }
+    }
+}
+
+// rows that were symbolically processed in chunks: nnz = popcount of the OR-ed bitmap
+__global__ void __launch_bounds__(128)
+k_sym_finish(const int32_t *__restrict__ rows, const int *__restrict__ item_off, int n_words,
+             const unsigned *__restrict__ keep, int32_t *__restrict__ row_nnz, int32_t *__restrict__ keep_slot)
+{
+    __shared__ int s_count;
+    const int idx = blockIdx.x;
+    if (item_off[idx + 1] - item_off[idx] <= 1)
+        return;
+    if (threadIdx.x == 0)
+        s_count = 0;
+    __syncthreads();
+    const unsigned *bm = keep + (size_t)idx * n_words;
+    int count = 0;
+    for (int i = threadIdx.x; i < n_words; i += 128)
+        count += __popc(bm[i]);
+    count = warp_sum(count);
+    if ((threadIdx.x & 31) == 0 && count)
+        atomicAdd(&s_count, count);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        row_nnz[rows[idx]] = s_count;
+        keep_slot[rows[idx]] = idx;
     }
 }
 
@@ -581,6 +652,7 @@ __global__ void __launch_bounds__(THREADS) k_num_dense(MatView A, MatView B, con
 // Lanes fetch the metadata of 32 A entries at once; the B pieces of OWN_DEPTH entries are in
 // flight before the first is consumed.
 constexpr int OWN_NW = 16, OWN_DEPTH = 16;
+constexpr int OWN_MAX_CHUNKS = 64;      // slices of one heavy row (A entries) handed to different CTAs
 
 __global__ void k_col_hist(const int32_t *__restrict__ ci, int64_t nnz, int *__restrict__ cnt)
 {
@@ -657,11 +729,12 @@ __global__ void __launch_bounds__(NW * 32, 1)
 k_num_owner(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, const int64_t *__restrict__ c_rp,
             int32_t *__restrict__ c_ci, double *__restrict__ c_vs, int both_f32, int n_cols, int win, int passes,
             int *__restrict__ work_counter, const unsigned *__restrict__ keep, const int32_t *__restrict__ keep_slot,
-            const int32_t *__restrict__ split)
+            const int32_t *__restrict__ split, const int *__restrict__ item_off, const int *__restrict__ chunk_base,
+            int nitems, double *__restrict__ partial)
 {
     constexpr int THREADS = NW * 32;
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int s_idx;
+    __shared__ int s_idx, s_ri;
     __shared__ int s_wt[33];
     double *acc = reinterpret_cast<double *>(s_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -670,14 +743,36 @@ k_num_owner(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
         acc[i] = 0.0;
     while (true) {
         __syncthreads();
-        if (tid == 0)
-            s_idx = atomicAdd(work_counter, 1);
+        if (tid == 0) {
+            // work item -> (row of the list, chunk of its A entries): last ri with item_off[ri] <= item
+            const int item = atomicAdd(work_counter, 1);
+            int lo = 0, hi = nbin;
+            if (item < nitems) {
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (item_off[mid] <= item)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+            }
+            s_idx = item;
+            s_ri = lo;
+        }
         __syncthreads();
-        const int idx = s_idx;
-        if (idx >= nbin)
+        if (s_idx >= nitems)
             break;
-        const int32_t row = rows[idx];
-        const int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+        const int ri = s_ri;
+        const int chunk = s_idx - item_off[ri], nch = item_off[ri + 1] - item_off[ri];
+        const int32_t row = rows[ri];
+        int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+        if (nch > 1) {
+            // a row with too many products for one CTA: this item takes one slice of its A entries and
+            // leaves its accumulator windows in `partial`; k_own_combine adds the slices in order
+            const int64_t len = ae - as;
+            ae = as + len * (chunk + 1) / nch;
+            as = as + len * chunk / nch;
+        }
         const unsigned *kept = keep + (size_t)keep_slot[row] * n_words;
         int64_t out = c_rp[row];
         for (int q = 0; q < passes; q++) {
@@ -756,6 +851,15 @@ k_num_owner(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
                 }
             }
             __syncthreads();
+            if (nch > 1) {
+                double *dst = partial + ((size_t)(chunk_base[ri] + chunk) * passes + q) * win;
+                for (int i = tid; i < win; i += THREADS) {
+                    dst[i] = acc[i];
+                    acc[i] = 0.0;
+                }
+                __syncthreads();
+                continue;
+            }
             // sweep the window in column order with the bitmap kept by the symbolic phase
             const int nw = (c1 - c0 + 31) >> 5;
             for (int wb = 0; wb < nw; wb += THREADS) {
@@ -777,6 +881,73 @@ k_num_owner(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
             }
             __syncthreads();
         }
+    }
+}
+
+// chunks per heavy row: rows with more than `chunk_prod` products are cut into slices of A entries
+__global__ void k_own_items(MatView A, const int32_t *__restrict__ rows, int n, const int64_t *__restrict__ prod,
+                            int64_t chunk_prod, int *__restrict__ nchunk, int *__restrict__ nsplit, int *__restrict__ last_split)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int32_t row = rows[i];
+    const int64_t len = ld_rp(A.rp, A.rp64, (int64_t)row + 1) - ld_rp(A.rp, A.rp64, row);
+    int64_t c = (prod[row] + chunk_prod - 1) / chunk_prod;
+    c = max((int64_t)1, min(min(c, len), (int64_t)OWN_MAX_CHUNKS));
+    nchunk[i] = (int)c;
+    nsplit[i] = c > 1 ? (int)c : 0;
+    if (c > 1)
+        atomicMax(last_split, i + 1);  // the list is LPT-ordered, so this stays near the number of chunked rows
+}
+
+// One CTA per (row of the list, window): rows that were cut into chunks get their partial windows
+// added in chunk order (deterministic) and are emitted through the kept bitmap like any other row.
+__global__ void __launch_bounds__(256)
+k_own_combine(const int32_t *__restrict__ rows, int nbin, const int *__restrict__ item_off,
+              const int *__restrict__ chunk_base, const double *__restrict__ partial, int n_cols, int win, int passes,
+              const unsigned *__restrict__ keep, const int32_t *__restrict__ keep_slot, const int64_t *__restrict__ c_rp,
+              int32_t *__restrict__ c_ci, double *__restrict__ c_vs)
+{
+    __shared__ int s_wt[33];
+    const int ri = blockIdx.x / passes, q = blockIdx.x % passes;
+    const int nch = item_off[ri + 1] - item_off[ri];
+    if (nch <= 1)
+        return;
+    const int tid = threadIdx.x;
+    const int32_t row = rows[ri];
+    const int n_words = (n_cols + 31) >> 5;
+    const unsigned *kept = keep + (size_t)keep_slot[row] * n_words;
+    const int c0 = q * win, c1 = min(c0 + win, n_cols);
+    // output position of the window's first entry: the row's kept columns below c0
+    int below = 0;
+    for (int i = tid; i < (c0 >> 5); i += 256)
+        below += __popc(kept[i]);
+    int tot;
+    block_exclusive_scan<int>(below, s_wt, tot);
+    int64_t out = c_rp[row] + tot;
+    __syncthreads();
+    const double *p0 = partial + ((size_t)chunk_base[ri] * passes + q) * win;
+    const size_t cstride = (size_t)passes * win;
+    const int nw = (c1 - c0 + 31) >> 5;
+    for (int wb = 0; wb < nw; wb += 256) {
+        const int i = wb + tid;
+        unsigned bits = i < nw ? kept[(c0 >> 5) + i] : 0u;
+        const int off = block_exclusive_scan<int>(__popc(bits), s_wt, tot);
+        int64_t o = out + off;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int kl = i * 32 + b;
+            double v = 0.0;
+            for (int ch = 0; ch < nch; ch++)
+                v = __dadd_rn(v, p0[ch * cstride + kl]);
+            c_ci[o] = c0 + kl;
+            c_vs[o] = v;
+            o++;
+        }
+        out += tot;
+        __syncthreads();
     }
 }
 
@@ -863,20 +1034,32 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     const size_t smem_max = ctx().smem_optin;
     const int n_words = (int)div_up(n, 32);
 
+    CSRK_TRACE_MARK("spgemm: enter", s);
     // ---- step 0: products per row
     DevBuf prod, total;
     CSRK_TRY(prod.alloc(sizeof(int64_t) * (size_t)m, s));
-    CSRK_TRY(total.alloc_zero(sizeof(unsigned long long), s));
+    CSRK_TRY(total.alloc_zero(sizeof(unsigned long long) * 2, s));
     CSRK_LAUNCH(k_row_products, (unsigned)div_up((int64_t)m * 32, 256), 256, 0, s, A, B, prod.as<int64_t>(),
                 total.as<unsigned long long>());
+    unsigned long long PM[2] = {0, 0};  // total products, products of the heaviest row (landed by bin_rows' sync)
+    CSRK_CUDA(cudaMemcpyAsync(PM, total.p, sizeof PM, cudaMemcpyDeviceToHost, s));
 
     // ---- step 1: symbolic
     BinSpec sspec{{0, SYM_WARP_SLOTS / 2, SYM_C1 / 2, SYM_C2 / 2, SYM_C3 / 2, INT64_MAX}};
     int cnt[NBINS], off[NBINS + 1];
     DevBuf list;
     CSRK_TRY(bin_rows(prod.as<int64_t>(), (int64_t)m, sspec, cnt, off, list, s));
-    unsigned long long P = 0;
-    CSRK_CUDA(cudaMemcpyAsync(&P, total.p, sizeof P, cudaMemcpyDeviceToHost, s));
+    const unsigned long long P = PM[0];
+    // Heavy rows are cut into chunks of A entries when the heaviest row alone would take more than half
+    // of an SM's fair share of the products (the top item of configs[2] is 20 M products = 51 ms on one
+    // CTA: the whole critical path of a multi-GPU run, where a rank's block is ~1/N of the products);
+    // chunks are 1/8 of the fair share.  "own_chunk_prod": 0 = that rule, > 0 = products per chunk
+    // (always chunk rows above it), < 0 = never chunk.
+    const int64_t opt_chunk = options().own_chunk_prod.load();
+    const int64_t fair = (int64_t)(P / (unsigned long long)sms) + 1;
+    const int64_t chunk_prod = opt_chunk > 0 ? opt_chunk : std::max<int64_t>(fair / 8, (int64_t)1 << 18);
+    const bool chunking = opt_chunk > 0 ? (int64_t)PM[1] > chunk_prod
+                                        : (opt_chunk == 0 && (int64_t)PM[1] > std::max<int64_t>(fair / 2, chunk_prod));
     DevBuf row_nnz;
     CSRK_TRY(row_nnz.alloc_zero(sizeof(int32_t) * (size_t)m, s));
     DevBuf counter;
@@ -905,21 +1088,40 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
             CSRK_TRY(keep.alloc(bm_bytes * (size_t)cnt[5], s));
             CSRK_TRY(keep_slot.alloc(sizeof(int32_t) * (size_t)m, s));
         }
+        // chunked symbolic rows OR into their kept bitmap, so chunking needs the kept bitmaps (zeroed)
+        DevBuf s_nchunk, s_nsplit, s_last, s_item_off;
+        const int *sio = nullptr;
+        if (chunking && keep.p) {
+            CSRK_TRY(s_nchunk.alloc(sizeof(int) * (size_t)cnt[5], s));
+            CSRK_TRY(s_nsplit.alloc(sizeof(int) * (size_t)cnt[5], s));
+            CSRK_TRY(s_last.alloc_zero(sizeof(int), s));
+            CSRK_TRY(s_item_off.alloc(sizeof(int) * ((size_t)cnt[5] + 1), s));
+            CSRK_LAUNCH(k_own_items, (unsigned)div_up(cnt[5], 256), 256, 0, s, A, L + off[5], cnt[5], prod.as<int64_t>(),
+                        chunk_prod, s_nchunk.as<int>(), s_nsplit.as<int>(), s_last.as<int>());
+            CSRK_TRY((exclusive_scan<int>(ArrayLoader<int>{s_nchunk.as<int>()}, (int64_t)cnt[5], s_item_off.as<int>(), s)));
+            CSRK_CUDA(cudaMemsetAsync(keep.p, 0, bm_bytes * (size_t)cnt[5], s));
+            sio = s_item_off.as<int>();
+        }
+        const int64_t max_items = (int64_t)cnt[5] + (sio ? (int64_t)sms * 8 + 1 : 0);
         if (bm_bytes + 1024 <= smem_max - 8 * 1024) {
             auto k = k_sym_bitmap<true, DENSE_THREADS>;
             CSRK_TRY(optin_smem(k, bm_bytes));
-            const int grid = (int)std::min((int64_t)cnt[5], (int64_t)sms * (bm_bytes > 100 * 1024 ? 1 : 2));
+            const int grid = (int)std::min(max_items, (int64_t)sms * (bm_bytes > 100 * 1024 ? 1 : 2));
             CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
-                        (unsigned *)nullptr, n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>());
+                        (unsigned *)nullptr, n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>(), sio);
         } else {
             auto k = k_sym_bitmap<false, DENSE_THREADS>;
-            const int grid = (int)std::min((int64_t)cnt[5], (int64_t)sms * 2);
+            const int grid = (int)std::min(max_items, (int64_t)sms * 2);
             CSRK_TRY(gbm.alloc_zero(bm_bytes * (size_t)grid, s));
             CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
-                        gbm.as<unsigned>(), n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>());
+                        gbm.as<unsigned>(), n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>(), sio);
         }
+        if (sio)
+            CSRK_LAUNCH(k_sym_finish, (unsigned)cnt[5], 128, 0, s, L + off[5], sio, n_words, keep.as<unsigned>(),
+                        row_nnz.as<int32_t>(), keep_slot.as<int32_t>());
     }
 
+    CSRK_TRACE_MARK("spgemm: products + symbolic", s);
     // ---- step 2: rowptrs
     DevBuf rp64;
     CSRK_TRY(rp64.alloc(sizeof(int64_t) * ((size_t)m + 1), s));
@@ -933,9 +1135,11 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     CSRK_TRY(bin_rows(row_nnz.as<int32_t>(), (int64_t)m, nspec, ncnt, noff, nlist, s));
     gbm.reset();
 
+    CSRK_TRACE_MARK("spgemm: rowptr scan + numeric bins", s);
     csrk_matrix *out = nullptr;
     const int rp_is64 = Z > (int64_t)INT32_MAX ? 1 : 0;
     CSRK_TRY(matrix_alloc(&out, m, n, Z, rp_is64, 8, s));
+    CSRK_TRACE_MARK("spgemm: result allocated", s);
     int rc = CSRK_OK;
     auto fail = [&](int code) {
         matrix_destroy(out, s);
@@ -972,6 +1176,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
             return fail(cuda_fail(ce, "lpt copy", __FILE__, __LINE__));
     }
 
+    CSRK_TRACE_MARK("spgemm: LPT order", s);
     // ---- step 3: numeric
     const int32_t *NL = nlist.as<int32_t>();
     const int64_t *crp = rp64.as<int64_t>();
@@ -1029,17 +1234,46 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                 CSRK_LAUNCH(k_own_split, (unsigned)div_up((int64_t)b->nrows * (nb + 1), 256), 256, 0, s, B,
                             bounds.as<int32_t>(), nb, split.as<int32_t>());
                 const size_t bytes = (size_t)win * 8;
-                const int grid = (int)std::min((int64_t)ncnt[5], (int64_t)sms);
+                // work items: a row, or one chunk of a heavy row's A entries (see chunk_prod above)
+                DevBuf nchunk, nsplit, item_off, chunk_base, partial, last_split;
+                CSRK_TRY(last_split.alloc_zero(sizeof(int), s));
+                CSRK_TRY(nchunk.alloc(sizeof(int) * (size_t)ncnt[5], s));
+                CSRK_TRY(nsplit.alloc(sizeof(int) * (size_t)ncnt[5], s));
+                CSRK_TRY(item_off.alloc(sizeof(int) * ((size_t)ncnt[5] + 1), s));
+                CSRK_TRY(chunk_base.alloc(sizeof(int) * ((size_t)ncnt[5] + 1), s));
+                CSRK_LAUNCH(k_own_items, (unsigned)div_up(ncnt[5], 256), 256, 0, s, A, NL + noff[5], ncnt[5], prod.as<int64_t>(),
+                            chunking ? chunk_prod : INT64_MAX / 2, nchunk.as<int>(), nsplit.as<int>(), last_split.as<int>());
+                CSRK_TRY((exclusive_scan<int>(ArrayLoader<int>{nchunk.as<int>()}, (int64_t)ncnt[5], item_off.as<int>(), s)));
+                CSRK_TRY((exclusive_scan<int>(ArrayLoader<int>{nsplit.as<int>()}, (int64_t)ncnt[5], chunk_base.as<int>(), s)));
+                int tots[3] = {0, 0, 0};
+                CSRK_CUDA(cudaMemcpyAsync(&tots[2], last_split.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+                CSRK_CUDA(cudaMemcpyAsync(&tots[0], item_off.as<int>() + ncnt[5], sizeof(int), cudaMemcpyDeviceToHost, s));
+                CSRK_CUDA(cudaMemcpyAsync(&tots[1], chunk_base.as<int>() + ncnt[5], sizeof(int), cudaMemcpyDeviceToHost, s));
+                CSRK_CUDA(cudaStreamSynchronize(s));
+                const int nitems = tots[0], nparts = tots[1];
+                if (nparts)
+                    CSRK_TRY(partial.alloc(sizeof(double) * (size_t)nparts * passes * win, s));
+                const int grid = (int)std::min((int64_t)nitems, (int64_t)sms);
+                CSRK_TRACE_MARK("spgemm: light bins + owner prep (hist, bounds, split, items)", s);
                 if (own_nw == 8) {
                     auto k = k_num_owner<8>;
                     CSRK_TRY(optin_smem(k, bytes));
                     CSRK_LAUNCH(k, (unsigned)grid, 8 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
-                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>());
+                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
+                                chunk_base.as<int>(), nitems, partial.as<double>());
                 } else {
                     auto k = k_num_owner<16>;
                     CSRK_TRY(optin_smem(k, bytes));
                     CSRK_LAUNCH(k, (unsigned)grid, 16 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
-                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>());
+                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
+                                chunk_base.as<int>(), nitems, partial.as<double>());
+                }
+                if (nparts) {
+                    CSRK_TRACE_MARK("spgemm: numeric (owner kernel)", s);
+                    // chunked rows sit at the head of the LPT-ordered list; a CTA of an unchunked row exits at once
+                    const int64_t ncomb = tots[2];
+                    CSRK_LAUNCH(k_own_combine, (unsigned)(ncomb * passes), 256, 0, s, NL + noff[5], ncnt[5], item_off.as<int>(),
+                                chunk_base.as<int>(), partial.as<double>(), (int)n, win, passes, kp, ks, crp, out->ci, cvs);
                 }
             } else if (passes <= DENSE_MAX_PASSES) {
                 const int win = (int)(div_up(div_up((int64_t)n, passes), 32) * 32);  // balanced windows
@@ -1065,6 +1299,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     rc = numeric();
     if (rc != CSRK_OK)
         return fail(rc);
+    CSRK_TRACE_MARK("spgemm: numeric", s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess)
         return fail(cuda_fail(e, "spgemm", __FILE__, __LINE__));

@@ -64,6 +64,9 @@ int csrk_synchronize(void);
 /* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 panel/slab kernel;
  * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan;
  * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
+ * "own_chunk_prod" SpGEMM: rows with more products than this are cut into chunks of A entries handled by
+ *               different CTAs and summed in chunk order (0 = 1/8 of an SM's fair share, < 0 = never:
+ *               every output element is then summed in the reference's own order, bit-identical values);
  * "radix_bits"  0 | 8 | 9 digit width of the stable sort behind transpose/order_columns
  *               (0 picks 9 when that saves a pass). */
 int csrk_set_option(const char *name, int64_t value);

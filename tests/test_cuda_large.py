@@ -194,25 +194,36 @@ def test_item_item_abt(kernel, dtype):
     _check_mm(kernel, M, M, True, 1e-10)
 
 
-def test_item_item_owner_path_is_bit_exact(kernel):
+@pytest.mark.parametrize("chunk_prod", [-1, 0, 60000])
+def test_item_item_owner_path(kernel, chunk_prod):
     """Rows with > 8192 output entries and a sorted (transposed) right operand take the
-    owner-computes dense kernel: no atomics, and every output element is summed in the
-    reference's own order, so the VALUES are bit-identical to the oracle too."""
+    owner-computes dense kernel: no atomics.  Unchunked (own_chunk_prod < 0; the default rule only
+    chunks when one row would be the critical path) every output element is summed in the
+    reference's own order, so the VALUES are bit-identical to the oracle too.  With heavy rows cut into chunks of A entries (symbolic and
+    numeric pass, forced here with 60000 products per chunk) the structure stays exact and the
+    values differ only by the order in which the chunk sums are added."""
     R = synth.powerlaw_csr(16000, 12000, 1_600_000, seed=81, dtype="f8", alpha=0.5, cap=600, min_len=20, col_skew=2.0)
     M = R.transpose()
     ref = orc.mult_abt(M, M)
     rp, ci, vs = canonical(ref)
     assert np.diff(rp).max() > 8192
+    kernel.set_option("own_chunk_prod", chunk_prod)
     mh = kernel.to_handle(M)
     try:
         ch = kernel.mult_abt(mh, mh)
         got = kernel.from_handle(ch)
+        st = kernel.spgemm_stats(ch)
         kernel.release_handle(ch)
     finally:
         kernel.release_handle(mh)
+        kernel.set_option("own_chunk_prod", 0)
     assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
+    assert st["out_nnz"] == ref.nnz
     heavy = np.repeat(np.diff(rp) > 8192, np.diff(rp))
-    assert np.array_equal(got.values[heavy], vs[heavy]), "owner path must reproduce the reference bit for bit"
+    if chunk_prod < 0:
+        assert np.array_equal(got.values[heavy], vs[heavy]), "owner path must reproduce the reference bit for bit"
+    elif chunk_prod > 0:
+        assert not np.array_equal(got.values[heavy], vs[heavy]), "chunking was requested but did not happen"
     assert_values_close(got.values, vs, 1e-10, float(np.abs(vs).max()))
 
 
