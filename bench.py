@@ -418,11 +418,11 @@ def cpu_model():
 
 def bench_spgemm(args, K, peak, rank, world, allmax, allsum):
     """A*A^T (item-item, BASELINE configs[2]): M = ratings^T, C = mult_abt(M, M).  With N GPUs
-    the rows of M are partitioned by products (strong scaling), M is replicated by NCCL broadcast
+    the rows of M are partitioned by a products + outputs cost model (strong scaling), M is replicated by NCCL broadcast
     and every rank multiplies its row block; output row blocks stay distributed."""
     import torch
     from csr_b200 import synth
-    from csr_b200.dist import replicate_csr, partition_by_weight
+    from csr_b200.dist import replicate_csr, partition_by_weight, spgemm_row_weights
     from oracle import oracle as orc
     R = synth.cfg3_ratings(args.spgemm_scale) if rank == 0 else None
     M = None
@@ -435,10 +435,9 @@ def bench_spgemm(args, K, peak, rank, world, allmax, allsum):
     t0 = time.perf_counter()
     M = replicate_csr(M, src=0)          # three NCCL broadcasts when world > 1
     t_bcast = time.perf_counter() - t0
-    lens = np.diff(M.rowptrs).astype(np.int64)
     user_len = np.bincount(M.colinds, minlength=M.ncols).astype(np.int64)
-    prod_row = np.add.reduceat(user_len[M.colinds], np.minimum(M.rowptrs[:-1].astype(np.int64), max(M.nnz - 1, 0))) * (lens > 0)
-    cuts = partition_by_weight(prod_row, world)
+    weight_row, prod_row = spgemm_row_weights(M, user_len, M.nrows)   # products + 0.45 x expected outputs
+    cuts = partition_by_weight(weight_row, world)
     mh = K.to_handle(M)
     ah = K.subset_rows(mh, cuts[rank], cuts[rank + 1]) if world > 1 else mh
 

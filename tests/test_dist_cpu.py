@@ -111,3 +111,20 @@ def test_world2_gloo():
         assert ok_mm, f"rank {rank}: assembled SpGEMM differs from the unsharded result"
         assert ok_rep, f"rank {rank}: replicated B differs"
         assert sum(counts) == 700
+
+
+def test_spgemm_row_weights_model():
+    """products per row (exact) and the products + 0.45 x expected-outputs weight used to cut A into rank blocks."""
+    from csr_b200 import synth
+    from csr_b200.dist import spgemm_row_weights, partition_by_weight
+    A = synth.powerlaw_csr(300, 200, 6000, seed=3, dtype="f8", alpha=0.8)
+    B = synth.powerlaw_csr(200, 150, 5000, seed=4, dtype="f8", alpha=0.8)
+    w, p = spgemm_row_weights(A, np.diff(B.rowptrs), B.ncols)
+    ref = np.array([np.diff(B.rowptrs)[A.colinds[A.rowptrs[i]:A.rowptrs[i + 1]]].sum() for i in range(A.nrows)])
+    assert np.array_equal(p, ref)
+    assert np.all(w >= p) and np.all(w <= p + 0.45 * np.minimum(p, B.ncols) + 1)
+    cuts = partition_by_weight(w, 4)
+    assert cuts[0] == 0 and cuts[-1] == A.nrows and all(cuts[i] <= cuts[i + 1] for i in range(4))
+    E = synth.powerlaw_csr(10, 20, 0, seed=1, dtype="f8")
+    w0, p0 = spgemm_row_weights(E, np.diff(B.rowptrs)[:20], 5)
+    assert w0.sum() == 0 and p0.sum() == 0
