@@ -327,7 +327,8 @@ def run_ours(args):
             "global_shape": [A.nrows * world, A.ncols], "global_nnz": A.nnz * world,
             "row_lengths": "rank-size power law alpha=1.0, mean 100, cap ncols, random row order",
             "columns": "stratified uniform" if args.col_skew == 1.0 else f"stratified, skew t^{args.col_skew}",
-            "parallelism": (f"row-partitioned x{world}; step = barrier + NVLS multicast copy of x (root) + barrier + SpMV "
+            "parallelism": "single GPU: step = the local SpMV (tile kernel + carry fix-up)" if world == 1 else
+                           (f"row-partitioned x{world}; step = NVLS multicast copy of x (root) + barrier + SpMV "
                             "kernel storing each finished y row once through the NVLink multicast address (fused "
                             "gather) + barrier") if ds.nvls is not None else
                            f"row-partitioned x{world}; step = NCCL broadcast(x) + " + (

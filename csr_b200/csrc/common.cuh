@@ -131,6 +131,7 @@ struct Options {
     std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab kernel v1, 3 cell-tile slab kernel
     std::atomic<int64_t> psf_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a slab plan
     std::atomic<int64_t> radix_bits{0};                 // digit width of the stable sort: 0 = pick (9 when it saves a pass), 8, 9
+    std::atomic<int64_t> spmv_zero_copy_y{1};           // csrk_spmv: store rows straight into pinned host y
     std::atomic<int64_t> own_chunk_prod{0};             // SpGEMM heavy-row chunking: 0 auto, > 0 products per chunk, < 0 off
     std::atomic<int64_t> own_nw{16};                    // warps (column ranges) per CTA in the owner-computes SpGEMM
 };

@@ -380,6 +380,8 @@ int csrk_set_option(const char *name, int64_t value)
     } else if (!strcmp(name, "radix_bits")) {
         CSRK_ARG(value == 0 || value == 8 || value == 9, "radix_bits must be 0, 8 or 9");
         options().radix_bits = value;
+    } else if (!strcmp(name, "spmv_zero_copy_y")) {
+        options().spmv_zero_copy_y = value ? 1 : 0;
     } else if (!strcmp(name, "own_chunk_prod")) {
         options().own_chunk_prod = value;
     } else if (!strcmp(name, "own_nw")) {
@@ -608,9 +610,26 @@ int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y)
     CSRK_TRY(dy.alloc((size_t)h->nrows * 8, s));
     if (h->ncols)
         CSRK_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)h->ncols * x_kind, cudaMemcpyHostToDevice, s));
-    CSRK_TRY(spmv_run(h, dx.p, x_kind, dy.as<double>(), s));
-    if (h->nrows)
-        CSRK_CUDA(cudaMemcpyAsync(y, dy.p, (size_t)h->nrows * 8, cudaMemcpyDeviceToHost, s));
+    // y in pinned (mapped) host memory: the kernel stores every finished row straight into it over PCIe
+    // as a second output, so the 8 B/row device-to-host copy overlaps the compute instead of following it
+    double *y_mapped = nullptr;
+    if (h->nrows && h->nnz && options().spmv_zero_copy_y.load()) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, y) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
+                y_mapped = (double *)at.devicePointer;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    if (y_mapped) {
+        double *ys[2] = {dy.as<double>(), y_mapped};
+        CSRK_TRY(spmv_run_multi(h, dx.p, x_kind, ys, 2, s, false));
+    } else {
+        CSRK_TRY(spmv_run(h, dx.p, x_kind, dy.as<double>(), s));
+        if (h->nrows)
+            CSRK_CUDA(cudaMemcpyAsync(y, dy.p, (size_t)h->nrows * 8, cudaMemcpyDeviceToHost, s));
+    }
     CSRK_CUDA(cudaStreamSynchronize(s));
     return CSRK_OK;
 }

@@ -59,10 +59,10 @@ struct YOut {
 };
 // `final` = the value is the row's result (not the head piece of a row that continues in later
 // tiles and gets its carries added by k_spmv_fixup): only final values leave the GPU.
-__device__ __forceinline__ void store_y(const YOut &y, int64_t r, double v, bool final)
+template <bool MULTI> __device__ __forceinline__ void store_y(const YOut &y, int64_t r, double v, bool final)
 {
     y.p[0][r] = v;
-    if (!final)
+    if (!MULTI || !final)
         return;
     if (y.mc) {
         asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(y.p[1] + r), "d"(v) : "memory");
@@ -101,7 +101,7 @@ __global__ void k_zero_f64(double *y, int64_t n)
         y[i] = 0.0;
 }
 
-template <typename RPT, typename VT, typename XT>
+template <typename RPT, typename VT, typename XT, bool MULTI>
 __global__ void __launch_bounds__(SPMV_BLOCK)
 k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_t *__restrict__ ci,
             const VT *__restrict__ vs, const XT *__restrict__ x, YOut y,
@@ -194,7 +194,7 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
             double s = 0.0;
             for (int i = s0; i < e0; i++)
                 s += (double)prod[i];
-            store_y(y, r, s, re <= tend);  // complete row, or the head piece of a row that continues (carries are added later)
+            store_y<MULTI>(y, r, s, re <= tend);  // complete row, or the head piece of a row that continues (carries are added later)
         }
     }
     __syncthreads();
@@ -209,13 +209,13 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
             s += (double)prod[i];
         s = warp_sum(s);
         if ((tid & 31) == 0)
-            store_y(y, r, s, re <= tend);
+            store_y<MULTI>(y, r, s, re <= tend);
     }
 }
 
 // One thread per tile t >= 1.  If tile t is the FIRST continuation tile of the row
 // that spills into it, add that row's carries in tile order: deterministic.
-template <typename RPT>
+template <typename RPT, bool MULTI>
 __global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict__ rp,
                              const int32_t *__restrict__ tile_row, const double *__restrict__ carry, YOut y)
 {
@@ -235,7 +235,7 @@ __global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict_
     double tot = 0.0;
     for (int64_t u = t; u <= tlast; u++)
         tot += carry[u];
-    store_y(y, row, y.p[0][row] + tot, true);
+    store_y<MULTI>(y, row, y.p[0][row] + tot, true);
 }
 
 static int ensure_plan(csrk_matrix *h, cudaStream_t s, SpmvPlan **out)
@@ -279,10 +279,18 @@ static int ensure_plan(csrk_matrix *h, cudaStream_t s, SpmvPlan **out)
 template <typename RPT, typename VT, typename XT>
 static int launch_spmv(csrk_matrix *h, SpmvPlan *p, const void *d_x, YOut d_y, double *carry, cudaStream_t s)
 {
-    CSRK_LAUNCH((k_spmv_tile<RPT, VT, XT>), (unsigned)p->ntiles, SPMV_BLOCK, 0, s, h->nrows, h->nnz,
+    if (d_y.n > 1) {
+        CSRK_LAUNCH((k_spmv_tile<RPT, VT, XT, true>), (unsigned)p->ntiles, SPMV_BLOCK, 0, s, h->nrows, h->nnz,
+                    (const RPT *)h->rp, h->ci, (const VT *)h->vs, (const XT *)d_x, d_y, p->tile_row, carry);
+        if (p->ntiles > 1)
+            CSRK_LAUNCH((k_spmv_fixup<RPT, true>), (unsigned)div_up(p->ntiles - 1, 256), 256, 0, s, p->ntiles, h->nnz,
+                        (const RPT *)h->rp, p->tile_row, carry, d_y);
+        return CSRK_OK;
+    }
+    CSRK_LAUNCH((k_spmv_tile<RPT, VT, XT, false>), (unsigned)p->ntiles, SPMV_BLOCK, 0, s, h->nrows, h->nnz,
                 (const RPT *)h->rp, h->ci, (const VT *)h->vs, (const XT *)d_x, d_y, p->tile_row, carry);
     if (p->ntiles > 1)
-        CSRK_LAUNCH((k_spmv_fixup<RPT>), (unsigned)div_up(p->ntiles - 1, 256), 256, 0, s, p->ntiles, h->nnz,
+        CSRK_LAUNCH((k_spmv_fixup<RPT, false>), (unsigned)div_up(p->ntiles - 1, 256), 256, 0, s, p->ntiles, h->nnz,
                     (const RPT *)h->rp, p->tile_row, carry, d_y);
     return CSRK_OK;
 }

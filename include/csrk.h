@@ -64,6 +64,7 @@ int csrk_synchronize(void);
 /* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 panel/slab kernel;
  * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan;
  * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
+ * "spmv_zero_copy_y" 1 | 0: csrk_spmv stores finished rows straight into y when y is pinned host memory;
  * "own_chunk_prod" SpGEMM: rows with more products than this are cut into chunks of A entries handled by
  *               different CTAs and summed in chunk order (0 = 1/8 of an SM's fair share, < 0 = never:
  *               every output element is then summed in the reference's own order, bit-identical values);
@@ -101,7 +102,9 @@ int csrk_subset_rows(csrk_h h, int32_t begin, int32_t end, csrk_h *out);
 
 /* ---- mult_vec: numba/__init__.py:55-67; lk_mkl_spmv, mkl_ops.h:29 --------
  * y[r] = sum_i x[colinds[i]] * (values[i] or 1), float64 accumulate, float64 y.
- * x_kind = 4 (float32) or 8 (float64).  Host pointers (pinned or pageable). */
+ * x_kind = 4 (float32) or 8 (float64).  Host pointers (pinned or pageable).  When y is pinned
+ * (cudaHostAlloc / cudaHostRegister, e.g. a torch pin_memory() tensor) the kernel writes each finished
+ * row directly into it over PCIe, overlapping the device-to-host transfer with the compute. */
 int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y);
 /* Device pointers; y has nrows doubles. */
 int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stream);

@@ -60,6 +60,27 @@ def test_spmv_empty_rows_and_tile_edges(kernel):
     assert np.all(y[lens == 0] == 0.0)
 
 
+def test_spmv_pinned_output_zero_copy(kernel):
+    """mult_vec(out=pinned): the kernel stores finished rows straight into the pinned host array
+    (second output of the tile kernel, carries included) -- same bits as the staged copy."""
+    import torch
+    A = synth.powerlaw_csr(60000, 50000, 3_000_000, seed=19, dtype="f4", alpha=1.0)  # rows spanning many tiles
+    x = synth.dense_vector(A.ncols, 5, "f4")
+    yp = torch.full((A.nrows,), float("nan"), dtype=torch.float64).pin_memory()
+    h = kernel.to_handle(A)
+    try:
+        y_staged = kernel.mult_vec(h, x)                      # pageable out: device buffer + D2H copy
+        y_pinned = kernel.mult_vec(h, x, out=yp.numpy())      # pinned out: zero-copy stores
+        kernel.set_option("spmv_zero_copy_y", 0)
+        y_off = kernel.mult_vec(h, x, out=torch.empty(A.nrows, dtype=torch.float64).pin_memory().numpy()).copy()
+    finally:
+        kernel.set_option("spmv_zero_copy_y", 1)
+        kernel.release_handle(h)
+    assert np.array_equal(y_pinned, y_staged) and np.array_equal(y_off, y_staged)
+    ref = orc.mult_vec(A, x)
+    assert_values_close(y_pinned, ref, 1e-5, _mv_scale(A, x))
+
+
 def test_spmv_linearity(kernel):
     A = synth.powerlaw_csr(2000, 3000, 100000, seed=31, dtype="f8", alpha=0.8)
     x1, x2 = synth.dense_vector(3000, 1, "f8"), synth.dense_vector(3000, 2, "f8")
