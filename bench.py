@@ -37,9 +37,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on
+# stdout), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the
+# saved original.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 PER_GPU_ROWS = 1_000_000
 PER_GPU_NNZ = 100_000_000
@@ -369,7 +377,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 def cpu_baseline_spmv(A, x, y_gpu):
@@ -522,7 +530,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     val = round(b / dt / 1e9, 3)
     sample = f"leading row block with {S.nnz} of {M.nnz} nnz per step, {cores} threads over row blocks"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "spmv_hbm_gbs", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 values/x, f64 accumulate", "data": "synthetic",
@@ -531,7 +539,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
                          "cpu": cpu_model()},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def main():
