@@ -132,6 +132,7 @@ struct Options {
     std::atomic<int64_t> psf_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a slab plan
     std::atomic<int64_t> radix_bits{0};                 // digit width of the stable sort: 0 = pick (9 when it saves a pass), 8, 9
     std::atomic<int64_t> spmv_zero_copy_y{1};           // csrk_spmv: store rows straight into pinned host y
+    std::atomic<int64_t> spgemm_fixed{1};               // SpGEMM heavy rows: fixed-point atomics when the value range allows
     std::atomic<int64_t> own_chunk_prod{0};             // SpGEMM heavy-row chunking: 0 auto, > 0 products per chunk, < 0 off
     std::atomic<int64_t> own_nw{16};                    // warps (column ranges) per CTA in the owner-computes SpGEMM
 };
@@ -149,6 +150,7 @@ struct csrk_matrix {
     void *vs = nullptr;     // float[nnz] / double[nnz] / nullptr
     int val_kind = 0;       // 0, 4, 8
     int64_t stat_products = -1, stat_out_nnz = -1;
+    int stat_path = 0;  // dense numeric path of the product that made this matrix: 0 none, 1 owner-computes, 2 fixed point
     csrk::SpmvPlan *plan = nullptr;  // lazily built SpMV tile map
     csrk::PsfPlan *psf[2] = {nullptr, nullptr};  // lazily built slab plans for float32 / float64 x
     bool psf_failed[2] = {false, false};

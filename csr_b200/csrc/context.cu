@@ -382,6 +382,8 @@ int csrk_set_option(const char *name, int64_t value)
         options().radix_bits = value;
     } else if (!strcmp(name, "spmv_zero_copy_y")) {
         options().spmv_zero_copy_y = value ? 1 : 0;
+    } else if (!strcmp(name, "spgemm_fixed")) {
+        options().spgemm_fixed = value ? 1 : 0;
     } else if (!strcmp(name, "own_chunk_prod")) {
         options().own_chunk_prod = value;
     } else if (!strcmp(name, "own_nw")) {
@@ -663,6 +665,13 @@ int csrk_spgemm_stats(csrk_h c, int64_t *products, int64_t *out_nnz)
     CSRK_ARG(c != nullptr, "NULL handle");
     if (products) *products = c->stat_products;
     if (out_nnz) *out_nnz = c->stat_out_nnz;
+    return CSRK_OK;
+}
+
+int csrk_spgemm_path(csrk_h c, int *path)
+{
+    CSRK_ARG(c != nullptr && path != nullptr, "NULL argument");
+    *path = c->stat_path;
     return CSRK_OK;
 }
 

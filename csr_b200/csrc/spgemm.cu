@@ -21,6 +21,8 @@
 // in float64, like multiply.py:120.  Only the summation ORDER differs from the
 // reference (hence rtol instead of bit-exact values).
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <type_traits>
 
 #include "radix.cuh"
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(256) k_row_products(MatView A, MatView B, int6
             if (p) {
                 atomicAdd(total, (unsigned long long)p);
                 atomicMax(total + 1, (unsigned long long)p);  // the heaviest row decides whether rows get chunked
+                atomicMax(total + 2, (unsigned long long)(e - s));  // longest row with products: sizes the fixed-point headroom
             }
         }
     }
@@ -653,6 +656,9 @@ __global__ void __launch_bounds__(THREADS) k_num_dense(MatView A, MatView B, con
 // flight before the first is consumed.
 constexpr int OWN_NW = 16, OWN_DEPTH = 16;
 constexpr int OWN_MAX_CHUNKS = 64;      // slices of one heavy row (A entries) handed to different CTAs
+constexpr int DENSE_THREADS = 512;
+constexpr int DENSE_WIN = 27648;                      // max columns per shared-memory accumulator window (216 KB)
+constexpr int DENSE_MAX_PASSES = 4;                   // beyond that: global scratch, one pass
 
 __global__ void k_col_hist(const int32_t *__restrict__ ci, int64_t nnz, int *__restrict__ cnt)
 {
@@ -951,6 +957,319 @@ k_own_combine(const int32_t *__restrict__ rows, int nbin, const int *__restrict_
     }
 }
 
+// ------------------------------------------- numeric: dense, 64-bit fixed point (native atomics)
+// Shared-memory float64 atomicAdd is a CAS loop (ATOMS.CAST.SPIN: 2.0 updates/clk/SM on random
+// columns, 0.5 with the hot columns of real rating data), the owner-computes kernel above avoids
+// atomics but leaves most lanes idle (0.24 products/clk/SM).  Native 32-bit ATOMS.ADD runs at ~10
+// updates/clk/SM (tools/micro/atoms.cu), so when the data allow it the accumulator is a 64-bit
+// two's-complement FIXED-POINT number per column, kept as two 32-bit words: the low word is added
+// with an atomicAdd that returns the old value (carry-out = unsigned overflow), the high word gets
+// its part plus the carry (4.3-5.1 updates/clk/SM).  Integer addition is associative: the result
+// does not depend on the order of the products, on how rows are chunked or on the number of GPUs.
+//
+// Scale of row i: 2^(e0 - hb_i) with hb_i = ceil(log2(len_i + 1)) bits of headroom for the at most
+// len_i terms of one output element and 2^e0 * max|a*b| <= 2^62.  Every term is rounded once to a
+// multiple of 2^-(e0-hb_i); spgemm_run only takes this path when all values are finite, non-negative
+// and max|a*b| / min|a*b| <= 2^(26-hb), which bounds the relative error of every output element by
+// 2^-35 = 2.9e-11 (rtol 1e-10 of the parity contract); anything else takes the owner kernel.
+struct ValStats {
+    unsigned long long min_bits, max_bits;  // bit patterns of the smallest non-zero and the largest |v|
+    int negative, nonfinite;
+};
+
+__global__ void __launch_bounds__(256) k_val_stats(const void *__restrict__ vs, int vk, int64_t nnz, ValStats *__restrict__ st)
+{
+    unsigned long long lo = ~0ull, hi = 0ull;
+    int neg = 0, bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = ld_val(vs, vk, i);
+        if (!isfinite(v))
+            bad = 1;
+        else if (v != 0.0) {
+            if (v < 0.0)
+                neg = 1;
+            const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
+            lo = min(lo, b);
+            hi = max(hi, b);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        neg |= __shfl_xor_sync(0xffffffffu, neg, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (hi) {
+            atomicMin(&st->min_bits, lo);
+            atomicMax(&st->max_bits, hi);
+        }
+        if (neg)
+            st->negative = 1;
+        if (bad)
+            st->nonfinite = 1;
+    }
+}
+
+__device__ __forceinline__ int headroom_bits(int64_t len)
+{
+    return 64 - __clzll((unsigned long long)len);  // ceil(log2(len + 1))
+}
+
+constexpr int FIX_MAX_PASSES = 4;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, const int64_t *__restrict__ c_rp,
+            int32_t *__restrict__ c_ci, double *__restrict__ c_vs, int both_f32, int n_cols, int win, int passes,
+            int *__restrict__ work_counter, const unsigned *__restrict__ keep, const int32_t *__restrict__ keep_slot,
+            const int32_t *__restrict__ psplit, const int *__restrict__ item_off, const int *__restrict__ chunk_base,
+            int nitems, long long *__restrict__ partial, int e0)
+{
+    static_assert(THREADS * 2 * 32 >= DENSE_WIN, "two bitmap words per thread must cover a window");
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ int s_idx, s_ri;
+    __shared__ int s_next[FIX_MAX_PASSES];
+    __shared__ int s_wt[33];
+    __shared__ unsigned s_bits[2 * THREADS];
+    __shared__ int s_wpre[2 * THREADS];
+    unsigned *slo = reinterpret_cast<unsigned *>(s_raw), *shi = slo + win;
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int NWARP = THREADS / 32;
+    const int n_words = (n_cols + 31) >> 5;
+    for (int i = tid; i < 2 * win; i += THREADS)
+        slo[i] = 0u;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            const int item = atomicAdd(work_counter, 1);
+            int lo = 0, hi = nbin;
+            if (item < nitems) {
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (item_off[mid] <= item)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+            }
+            s_idx = item;
+            s_ri = lo;
+        }
+        if (tid < FIX_MAX_PASSES)
+            s_next[tid] = 0;
+        __syncthreads();
+        if (s_idx >= nitems)
+            break;
+        const int ri = s_ri;
+        const int chunk = s_idx - item_off[ri], nch = item_off[ri + 1] - item_off[ri];
+        const int32_t row = rows[ri];
+        int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+        const int sh = e0 - headroom_bits(ae - as);  // the WHOLE row's length: all chunks share one scale
+        const double scale = __longlong_as_double((long long)(1023 + sh) << 52);   // 2^sh
+        const double inv_scale = __longlong_as_double((long long)(1023 - sh) << 52);
+        if (nch > 1) {
+            const int64_t len = ae - as;
+            ae = as + len * (chunk + 1) / nch;
+            as = as + len * chunk / nch;
+        }
+        const unsigned *kept = keep + (size_t)keep_slot[row] * n_words;
+        int64_t out = c_rp[row];
+        // batches of A entries are handed to the warps dynamically (pieces differ a lot in length)
+        const int bsz = (int)max((int64_t)1, min((int64_t)32, (ae - as + 2 * NWARP - 1) / (2 * NWARP)));
+        const int nbatch = (int)((ae - as + bsz - 1) / bsz);
+        for (int q = 0; q < passes; q++) {
+            const int c0 = q * win, c1 = min(c0 + win, n_cols);
+            const int nw = (c1 - c0 + 31) >> 5;
+            // the window's kept-bitmap words are fetched now and used after the accumulation
+            const unsigned kb0 = tid < nw ? kept[(c0 >> 5) + tid] : 0u;
+            const unsigned kb1 = THREADS + tid < nw ? kept[(c0 >> 5) + THREADS + tid] : 0u;
+            while (true) {
+                int bi = 0;
+                if (lane == 0)
+                    bi = atomicAdd(&s_next[q], 1);
+                bi = __shfl_sync(0xffffffffu, bi, 0);
+                if (bi >= nbatch)
+                    break;
+                const int64_t base = as + (int64_t)bi * bsz;
+                int64_t bs = 0;
+                int len = 0;
+                double av = 0.0;
+                if (lane < bsz && base + lane < ae) {
+                    const int32_t j = A.ci[base + lane];
+                    av = ld_val(A.vs, A.vk, base + lane);
+                    const int32_t *sp = psplit + (size_t)j * (passes + 1) + q;
+                    const int o0 = sp[0];
+                    len = sp[1] - o0;
+                    bs = ld_rp(B.rp, B.rp64, j) + o0;
+                }
+                const int cnt = (int)min((int64_t)bsz, ae - base);
+                // software pipeline over the pieces: the first 128 entries of piece t+1 are in flight
+                // while piece t goes through the atomics
+                int ncol[4];
+                double nval[4];
+                int64_t nbs = __shfl_sync(0xffffffffu, bs, 0);
+                int nlen = __shfl_sync(0xffffffffu, len, 0);
+                double nav = __shfl_sync(0xffffffffu, av, 0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = u * 32 + lane;
+                    ncol[u] = -1;
+                    if (k < nlen) {
+                        ncol[u] = B.ci[nbs + k];
+                        nval[u] = ld_val(B.vs, B.vk, nbs + k);
+                    }
+                }
+                for (int t = 0; t < cnt; t++) {
+                    int col[4];
+                    double val[4];
+                    const int64_t pbs = nbs;
+                    const int plen = nlen;
+                    const double pav = nav;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        col[u] = ncol[u];
+                        val[u] = nval[u];
+                    }
+                    if (t + 1 < cnt) {
+                        nbs = __shfl_sync(0xffffffffu, bs, t + 1);
+                        nlen = __shfl_sync(0xffffffffu, len, t + 1);
+                        nav = __shfl_sync(0xffffffffu, av, t + 1);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int k = u * 32 + lane;
+                            ncol[u] = -1;
+                            if (k < nlen) {
+                                ncol[u] = B.ci[nbs + k];
+                                nval[u] = ld_val(B.vs, B.vk, nbs + k);
+                            }
+                        }
+                    }
+                    for (int k0 = 0; k0 < plen; k0 += 128) {
+                        if (k0) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int k = k0 + u * 32 + lane;
+                                col[u] = -1;
+                                if (k < plen) {
+                                    col[u] = B.ci[pbs + k];
+                                    val[u] = ld_val(B.vs, B.vk, pbs + k);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (col[u] >= 0) {
+                                const long long T = __double2ll_rn(product(pav, val[u], both_f32) * scale);
+                                if (T) {
+                                    const int kl = col[u] - c0;
+                                    const unsigned tlo = (unsigned)T, thi = (unsigned)((unsigned long long)T >> 32);
+                                    const unsigned old = atomicAdd(&slo[kl], tlo);
+                                    atomicAdd(&shi[kl], thi + ((old + tlo) < old ? 1u : 0u));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (nch > 1) {
+                long long *dst = partial + ((size_t)(chunk_base[ri] + chunk) * passes + q) * win;
+                for (int i = tid; i < win; i += THREADS) {
+                    dst[i] = (long long)(((unsigned long long)shi[i] << 32) | slo[i]);
+                    slo[i] = 0u;
+                    shi[i] = 0u;
+                }
+                __syncthreads();
+                continue;
+            }
+            // sweep: one thread per COLUMN, so that a warp writes consecutive output slots; the slot of
+            // a column = kept bits below it (per-word prefix from a block scan + popcount inside the word)
+            int tot0, tot1;
+            const int ex0 = block_exclusive_scan<int>(__popc(kb0), s_wt, tot0);
+            __syncthreads();
+            const int ex1 = block_exclusive_scan<int>(__popc(kb1), s_wt, tot1);
+            s_bits[tid] = kb0;
+            s_bits[THREADS + tid] = kb1;
+            s_wpre[tid] = ex0;
+            s_wpre[THREADS + tid] = tot0 + ex1;
+            __syncthreads();
+            for (int col = tid; col < c1 - c0; col += THREADS) {
+                const unsigned bits = s_bits[col >> 5];
+                const unsigned bit = 1u << (col & 31);
+                if (bits & bit) {
+                    const int64_t o = out + s_wpre[col >> 5] + __popc(bits & (bit - 1u));
+                    const long long v = (long long)(((unsigned long long)shi[col] << 32) | slo[col]);
+                    c_ci[o] = c0 + col;
+                    c_vs[o] = (double)v * inv_scale;
+                    slo[col] = 0u;
+                    shi[col] = 0u;
+                }
+            }
+            out += tot0 + tot1;
+            __syncthreads();
+        }
+    }
+}
+
+// chunked rows of the fixed-point kernel: exact integer sum of the chunks' windows, then the scale
+__global__ void __launch_bounds__(256)
+k_fix_combine(MatView A, const int32_t *__restrict__ rows, int nbin, const int *__restrict__ item_off,
+              const int *__restrict__ chunk_base, const long long *__restrict__ partial, int n_cols, int win, int passes,
+              const unsigned *__restrict__ keep, const int32_t *__restrict__ keep_slot, const int64_t *__restrict__ c_rp,
+              int32_t *__restrict__ c_ci, double *__restrict__ c_vs, int e0)
+{
+    __shared__ int s_wt[33];
+    const int ri = blockIdx.x / passes, q = blockIdx.x % passes;
+    const int nch = item_off[ri + 1] - item_off[ri];
+    if (nch <= 1)
+        return;
+    const int tid = threadIdx.x;
+    const int32_t row = rows[ri];
+    const int sh = e0 - headroom_bits(ld_rp(A.rp, A.rp64, (int64_t)row + 1) - ld_rp(A.rp, A.rp64, row));
+    const double inv_scale = __longlong_as_double((long long)(1023 - sh) << 52);
+    const int n_words = (n_cols + 31) >> 5;
+    const unsigned *kept = keep + (size_t)keep_slot[row] * n_words;
+    const int c0 = q * win, c1 = min(c0 + win, n_cols);
+    int below = 0;
+    for (int i = tid; i < (c0 >> 5); i += 256)
+        below += __popc(kept[i]);
+    int tot;
+    block_exclusive_scan<int>(below, s_wt, tot);
+    int64_t out = c_rp[row] + tot;
+    __syncthreads();
+    const long long *p0 = partial + ((size_t)chunk_base[ri] * passes + q) * win;
+    const size_t cstride = (size_t)passes * win;
+    const int nw = (c1 - c0 + 31) >> 5;
+    for (int wb = 0; wb < nw; wb += 256) {
+        const int i = wb + tid;
+        unsigned bits = i < nw ? kept[(c0 >> 5) + i] : 0u;
+        const int off = block_exclusive_scan<int>(__popc(bits), s_wt, tot);
+        int64_t o = out + off;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int kl = i * 32 + b;
+            long long v = 0;
+            for (int ch = 0; ch < nch; ch++)
+                v += p0[ch * cstride + kl];
+            c_ci[o] = c0 + kl;
+            c_vs[o] = (double)v * inv_scale;
+            o++;
+        }
+        out += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void k_fix_bounds(int n, int win, int passes, int32_t *__restrict__ bounds)
+{
+    const int i = threadIdx.x;
+    if (i <= passes)
+        bounds[i] = i == passes ? n : min(i * win, n);
+}
+
 // sort key for longest-processing-time-first scheduling of the heavy rows: descending products
 __global__ void k_lpt_keys(const int32_t *__restrict__ rows, int n, const int64_t *__restrict__ prod, int32_t *__restrict__ keys)
 {
@@ -1000,9 +1319,6 @@ template <typename K> static int optin_smem(K kernel, size_t bytes)
 // through the symbolic bitmap kernel and can reuse its stored bitmap.
 constexpr int SYM_WARP_SLOTS = 256, SYM_C1 = 2048, SYM_C2 = 8192, SYM_C3 = 16384;
 constexpr int NUM_WARP_SLOTS = 128, NUM_C1 = 1024, NUM_C2 = 4096, NUM_C3 = 16384;
-constexpr int DENSE_THREADS = 512;
-constexpr int DENSE_WIN = 28160;                      // max columns per shared-memory accumulator window (220 KB)
-constexpr int DENSE_MAX_PASSES = 4;                   // beyond that: global scratch, one pass
 constexpr size_t KEEP_BITMAP_BUDGET = (size_t)8 << 30;  // bytes of symbolic bitmaps kept for the numeric phase
 
 static int make_empty_result(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
@@ -1038,10 +1354,10 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     // ---- step 0: products per row
     DevBuf prod, total;
     CSRK_TRY(prod.alloc(sizeof(int64_t) * (size_t)m, s));
-    CSRK_TRY(total.alloc_zero(sizeof(unsigned long long) * 2, s));
+    CSRK_TRY(total.alloc_zero(sizeof(unsigned long long) * 3, s));
     CSRK_LAUNCH(k_row_products, (unsigned)div_up((int64_t)m * 32, 256), 256, 0, s, A, B, prod.as<int64_t>(),
                 total.as<unsigned long long>());
-    unsigned long long PM[2] = {0, 0};  // total products, products of the heaviest row (landed by bin_rows' sync)
+    unsigned long long PM[3] = {0, 0, 0};  // total products, products of the heaviest row, longest row (landed by bin_rows' sync)
     CSRK_CUDA(cudaMemcpyAsync(PM, total.p, sizeof PM, cudaMemcpyDeviceToHost, s));
 
     // ---- step 1: symbolic
@@ -1207,30 +1523,65 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
             const int32_t *ks = keep_slot.as<int32_t>();
             const int passes = (int)div_up((int64_t)n, DENSE_WIN);
             bool owner = passes <= DENSE_MAX_PASSES && kp != nullptr && n >= 1024;
+            bool fixed = false;
+            int e0 = 0;
             if (owner) {
-                // owner-computes needs B's rows strictly increasing in column
-                DevBuf flag;
+                // both dense kernels walk B's rows by column range: rows strictly increasing in column
+                DevBuf flag, vstats;
                 CSRK_TRY(flag.alloc_zero(sizeof(int), s));
                 if (b->nnz > 1)
                     CSRK_LAUNCH(k_rows_not_strict, (unsigned)div_up(b->nnz - 1, 256), 256, 0, s, B, flag.as<int>());
+                // value range of both operands: decides whether the fixed-point accumulator is exact enough
+                const bool want_fixed = options().spgemm_fixed.load() != 0;
+                ValStats vs_h[2] = {{~0ull, 0ull, 0, 0}, {~0ull, 0ull, 0, 0}};
+                if (want_fixed) {
+                    CSRK_TRY(vstats.alloc(sizeof vs_h, s));
+                    CSRK_CUDA(cudaMemcpyAsync(vstats.p, vs_h, sizeof vs_h, cudaMemcpyHostToDevice, s));
+                    CSRK_LAUNCH(k_val_stats, (unsigned)std::min<int64_t>(div_up(a->nnz, 256), (int64_t)sms * 8), 256, 0, s, a->vs,
+                                a->val_kind, a->nnz, vstats.as<ValStats>());
+                    CSRK_LAUNCH(k_val_stats, (unsigned)std::min<int64_t>(div_up(b->nnz, 256), (int64_t)sms * 8), 256, 0, s, b->vs,
+                                b->val_kind, b->nnz, vstats.as<ValStats>() + 1);
+                    CSRK_CUDA(cudaMemcpyAsync(vs_h, vstats.p, sizeof vs_h, cudaMemcpyDeviceToHost, s));
+                }
                 int bad = 0;
                 CSRK_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
                 CSRK_CUDA(cudaStreamSynchronize(s));
                 owner = !bad;
+                if (owner && want_fixed && !vs_h[0].negative && !vs_h[1].negative && !vs_h[0].nonfinite && !vs_h[1].nonfinite &&
+                    vs_h[0].max_bits && vs_h[1].max_bits) {
+                    double lim[4];
+                    const unsigned long long bits[4] = {vs_h[0].min_bits, vs_h[0].max_bits, vs_h[1].min_bits, vs_h[1].max_bits};
+                    memcpy(lim, bits, sizeof lim);
+                    const double pmin = lim[0] * lim[2], pmax = lim[1] * lim[3];
+                    int hb = 0;
+                    for (unsigned long long l = PM[2]; l; l >>= 1)
+                        hb++;  // ceil(log2(longest row + 1)): terms per output element
+                    int x = 0;
+                    (void)frexp(pmax, &x);  // pmax <= 2^x
+                    // relative error of an output element <= (pmax / pmin) * 2^(hb - 61); keep it below 2^-35
+                    if (hb <= 24 && passes <= FIX_MAX_PASSES && pmin > 1e-280 && pmax < 1e280 && pmax / pmin <= ldexp(1.0, 26 - hb)) {
+                        fixed = true;
+                        e0 = 62 - x;
+                    }
+                }
             }
             if (owner) {
                 const int win = (int)(div_up(div_up((int64_t)n, passes), 32) * 32);
                 const int own_nw = options().own_nw.load() == 8 ? 8 : 16;
-                const int nb = passes * own_nw;
+                const int nb = fixed ? passes : passes * own_nw;
                 DevBuf hist, cum, bounds, split;
-                CSRK_TRY(hist.alloc_zero(sizeof(int) * ((size_t)n + 1), s));
-                CSRK_TRY(cum.alloc(sizeof(int64_t) * ((size_t)n + 1), s));
                 CSRK_TRY(bounds.alloc(sizeof(int32_t) * ((size_t)nb + 1), s));
                 CSRK_TRY(split.alloc(sizeof(int32_t) * (size_t)b->nrows * (nb + 1), s));
-                CSRK_LAUNCH(k_col_hist, (unsigned)div_up(b->nnz, 256), 256, 0, s, b->ci, b->nnz, hist.as<int>());
-                CSRK_TRY((exclusive_scan<int64_t>(ArrayLoader<int>{hist.as<int>()}, (int64_t)n, cum.as<int64_t>(), s)));
-                CSRK_LAUNCH(k_own_bounds, (unsigned)div_up(nb + 1, 64), 64, 0, s, cum.as<int64_t>(), (int)n, win, passes, own_nw,
-                            bounds.as<int32_t>());
+                if (fixed) {
+                    CSRK_LAUNCH(k_fix_bounds, 1u, 32, 0, s, (int)n, win, passes, bounds.as<int32_t>());
+                } else {
+                    CSRK_TRY(hist.alloc_zero(sizeof(int) * ((size_t)n + 1), s));
+                    CSRK_TRY(cum.alloc(sizeof(int64_t) * ((size_t)n + 1), s));
+                    CSRK_LAUNCH(k_col_hist, (unsigned)div_up(b->nnz, 256), 256, 0, s, b->ci, b->nnz, hist.as<int>());
+                    CSRK_TRY((exclusive_scan<int64_t>(ArrayLoader<int>{hist.as<int>()}, (int64_t)n, cum.as<int64_t>(), s)));
+                    CSRK_LAUNCH(k_own_bounds, (unsigned)div_up(nb + 1, 64), 64, 0, s, cum.as<int64_t>(), (int)n, win, passes,
+                                own_nw, bounds.as<int32_t>());
+                }
                 CSRK_LAUNCH(k_own_split, (unsigned)div_up((int64_t)b->nrows * (nb + 1), 256), 256, 0, s, B,
                             bounds.as<int32_t>(), nb, split.as<int32_t>());
                 const size_t bytes = (size_t)win * 8;
@@ -1254,26 +1605,41 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                 if (nparts)
                     CSRK_TRY(partial.alloc(sizeof(double) * (size_t)nparts * passes * win, s));
                 const int grid = (int)std::min((int64_t)nitems, (int64_t)sms);
-                CSRK_TRACE_MARK("spgemm: light bins + owner prep (hist, bounds, split, items)", s);
-                if (own_nw == 8) {
-                    auto k = k_num_owner<8>;
+                const int64_t ncomb = tots[2];  // chunked rows sit at the head of the LPT-ordered list
+                CSRK_TRACE_MARK("spgemm: light bins + dense prep (value range, bounds, split, items)", s);
+                if (fixed) {
+                    auto k = k_num_fixed<DENSE_THREADS>;
                     CSRK_TRY(optin_smem(k, bytes));
-                    CSRK_LAUNCH(k, (unsigned)grid, 8 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                    CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                                 (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
-                                chunk_base.as<int>(), nitems, partial.as<double>());
+                                chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                    if (nparts) {
+                        CSRK_TRACE_MARK("spgemm: numeric (fixed-point kernel)", s);
+                        CSRK_LAUNCH(k_fix_combine, (unsigned)(ncomb * passes), 256, 0, s, A, NL + noff[5], ncnt[5],
+                                    item_off.as<int>(), chunk_base.as<int>(), partial.as<long long>(), (int)n, win, passes, kp,
+                                    ks, crp, out->ci, cvs, e0);
+                    }
+                    out->stat_path = 2;
                 } else {
-                    auto k = k_num_owner<16>;
-                    CSRK_TRY(optin_smem(k, bytes));
-                    CSRK_LAUNCH(k, (unsigned)grid, 16 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
-                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
-                                chunk_base.as<int>(), nitems, partial.as<double>());
-                }
-                if (nparts) {
-                    CSRK_TRACE_MARK("spgemm: numeric (owner kernel)", s);
-                    // chunked rows sit at the head of the LPT-ordered list; a CTA of an unchunked row exits at once
-                    const int64_t ncomb = tots[2];
-                    CSRK_LAUNCH(k_own_combine, (unsigned)(ncomb * passes), 256, 0, s, NL + noff[5], ncnt[5], item_off.as<int>(),
-                                chunk_base.as<int>(), partial.as<double>(), (int)n, win, passes, kp, ks, crp, out->ci, cvs);
+                    if (own_nw == 8) {
+                        auto k = k_num_owner<8>;
+                        CSRK_TRY(optin_smem(k, bytes));
+                        CSRK_LAUNCH(k, (unsigned)grid, 8 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                                    (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
+                                    chunk_base.as<int>(), nitems, partial.as<double>());
+                    } else {
+                        auto k = k_num_owner<16>;
+                        CSRK_TRY(optin_smem(k, bytes));
+                        CSRK_LAUNCH(k, (unsigned)grid, 16 * 32, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                                    (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
+                                    chunk_base.as<int>(), nitems, partial.as<double>());
+                    }
+                    if (nparts) {
+                        CSRK_TRACE_MARK("spgemm: numeric (owner kernel)", s);
+                        CSRK_LAUNCH(k_own_combine, (unsigned)(ncomb * passes), 256, 0, s, NL + noff[5], ncnt[5], item_off.as<int>(),
+                                    chunk_base.as<int>(), partial.as<double>(), (int)n, win, passes, kp, ks, crp, out->ci, cvs);
+                    }
+                    out->stat_path = 1;
                 }
             } else if (passes <= DENSE_MAX_PASSES) {
                 const int win = (int)(div_up(div_up((int64_t)n, passes), 32) * 32);  // balanced windows

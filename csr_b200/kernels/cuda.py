@@ -215,7 +215,10 @@ def spgemm_stats(h: cuda_h) -> dict:
     """Products P and out-nnz Z of the multiplication that produced ``h``."""
     p, z = C.c_int64(), C.c_int64()
     N.check(N.lib().csrk_spgemm_stats(_live(h), C.byref(p), C.byref(z)), "spgemm_stats")
-    return {"products": p.value, "out_nnz": z.value}
+    path = C.c_int()
+    N.check(N.lib().csrk_spgemm_path(_live(h), C.byref(path)), "spgemm_path")
+    return {"products": p.value, "out_nnz": z.value,
+            "dense_path": {0: "none", 1: "owner", 2: "fixed"}.get(path.value, str(path.value))}
 
 
 def mult_vec_dev(h: cuda_h, x_ptr: int, x_itemsize: int, y_ptr: int, stream: int = 0) -> None:

@@ -65,6 +65,7 @@ int csrk_synchronize(void);
  * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan;
  * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
  * "spmv_zero_copy_y" 1 | 0: csrk_spmv stores finished rows straight into y when y is pinned host memory;
+ * "spgemm_fixed" 1 | 0: allow the fixed-point numeric kernel for heavy rows (see csrk_spgemm_path);
  * "own_chunk_prod" SpGEMM: rows with more products than this are cut into chunks of A entries handled by
  *               different CTAs and summed in chunk order (0 = 1/8 of an SM's fair share, < 0 = never:
  *               every output element is then summed in the reference's own order, bit-identical values);
@@ -132,6 +133,12 @@ int csrk_spgemm_abt(csrk_h a, csrk_h b, csrk_h *c);
 /* Work counters of the last product that produced `c`: products P (sum over
  * A's entries of the referenced B row length) and out-nnz Z. */
 int csrk_spgemm_stats(csrk_h c, int64_t *products, int64_t *out_nnz);
+/* Which numeric kernel handled the heavy (dense-accumulator) rows of the product that made c:
+ * 0 none / the general dense kernels, 1 owner-computes (float64, reference summation order),
+ * 2 64-bit fixed point on native shared-memory atomics (order-independent, only taken when all values
+ * are finite and non-negative and max|a*b|/min|a*b| <= 2^(26 - ceil(log2(longest row + 1))), which keeps
+ * every output element within 2^-35 of the exact sum; "spgemm_fixed" = 0 disables it). */
+int csrk_spgemm_path(csrk_h c, int *path);
 
 /* ---- transpose: csr/structure.py:172-247 ---------------------------------
  * Stable CSR->CSC.  rowptr dtype follows the input; values become float64

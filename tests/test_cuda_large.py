@@ -229,6 +229,7 @@ def test_item_item_owner_path(kernel, chunk_prod):
     rp, ci, vs = canonical(ref)
     assert np.diff(rp).max() > 8192
     kernel.set_option("own_chunk_prod", chunk_prod)
+    kernel.set_option("spgemm_fixed", 0)   # positive ratings would otherwise take the fixed-point kernel
     mh = kernel.to_handle(M)
     try:
         ch = kernel.mult_abt(mh, mh)
@@ -238,14 +239,73 @@ def test_item_item_owner_path(kernel, chunk_prod):
     finally:
         kernel.release_handle(mh)
         kernel.set_option("own_chunk_prod", 0)
+        kernel.set_option("spgemm_fixed", 1)
     assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
-    assert st["out_nnz"] == ref.nnz
+    assert st["out_nnz"] == ref.nnz and st["dense_path"] == "owner"
     heavy = np.repeat(np.diff(rp) > 8192, np.diff(rp))
     if chunk_prod < 0:
         assert np.array_equal(got.values[heavy], vs[heavy]), "owner path must reproduce the reference bit for bit"
     elif chunk_prod > 0:
         assert not np.array_equal(got.values[heavy], vs[heavy]), "chunking was requested but did not happen"
     assert_values_close(got.values, vs, 1e-10, float(np.abs(vs).max()))
+
+
+def _abt(kernel, M, **opts):
+    for k, v in opts.items():
+        kernel.set_option(k, v)
+    mh = kernel.to_handle(M)
+    try:
+        ch = kernel.mult_abt(mh, mh)
+        got = kernel.from_handle(ch)
+        st = kernel.spgemm_stats(ch)
+        kernel.release_handle(ch)
+    finally:
+        kernel.release_handle(mh)
+        kernel.set_option("own_chunk_prod", 0)
+        kernel.set_option("spgemm_fixed", 1)
+    return got, st
+
+
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
+def test_item_item_fixed_point_path(kernel, dtype):
+    """Non-negative values of bounded range (ratings): heavy rows are accumulated in 64-bit fixed point with
+    native shared-memory atomics.  Structure exact; EVERY value within rtol 1e-10 (f64) of the oracle with
+    no absolute slack; and, integer sums being order-independent, cutting rows into chunks changes nothing."""
+    R = synth.powerlaw_csr(16000, 12000, 1_600_000, seed=81, dtype=dtype, alpha=0.5, cap=600, min_len=20, col_skew=2.0)
+    M = R.transpose()            # values become float64 (of float32 ratings for "f4")
+    ref = orc.mult_abt(M, M)
+    rp, ci, vs = canonical(ref)
+    got, st = _abt(kernel, M)
+    assert st["dense_path"] == "fixed"
+    assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
+    assert np.allclose(got.values, vs, rtol=1e-10, atol=0.0)
+    chunked, st2 = _abt(kernel, M, own_chunk_prod=60000)
+    assert st2["dense_path"] == "fixed"
+    heavy = np.repeat(np.diff(rp) > 8192, np.diff(rp))   # (lighter rows use float64 hash accumulators: order varies)
+    assert np.array_equal(chunked.colinds, got.colinds) and np.array_equal(chunked.values[heavy], got.values[heavy])
+    assert np.allclose(chunked.values, vs, rtol=1e-10, atol=0.0)
+
+
+@pytest.mark.parametrize("case", ["negative", "wide_range", "nonfinite"])
+def test_fixed_point_gate_falls_back_to_owner(kernel, case):
+    """The fixed-point kernel is only taken when its error bound holds: mixed signs, a wide dynamic range or a
+    non-finite value send the heavy rows to the owner-computes kernel (bit-identical to the oracle)."""
+    R = synth.powerlaw_csr(16000, 12000, 1_600_000, seed=81, dtype="f8", alpha=0.5, cap=600, min_len=20, col_skew=2.0)
+    v = R.values.copy()
+    if case == "negative":
+        v[::7] *= -1.0
+    elif case == "wide_range":
+        v[::5] *= 1e-7
+    else:
+        v[12345] = np.inf
+    M = CSR(R.nrows, R.ncols, R.nnz, R.rowptrs, R.colinds, v).transpose()
+    ref = orc.mult_abt(M, M)
+    rp, ci, vs = canonical(ref)
+    got, st = _abt(kernel, M, own_chunk_prod=-1)
+    assert st["dense_path"] == "owner"
+    assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
+    heavy = np.repeat(np.diff(rp) > 8192, np.diff(rp))
+    assert np.array_equal(got.values[heavy], vs[heavy], equal_nan=True)
 
 
 def test_virtual_ranks_row_blocks(kernel):

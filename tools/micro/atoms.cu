@@ -1,0 +1,63 @@
+// Microbenchmark: shared-memory atomic throughput on B200 (random addresses in a 25k-entry window).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+constexpr int WIN = 25600;
+template <int MODE> __global__ void __launch_bounds__(512, 1) k(int iters, unsigned long long *sink, int skew = 0)
+{
+    extern __shared__ unsigned char raw[];
+    int *a32 = (int *)raw;
+    double *a64 = (double *)raw;
+    const int n = MODE == 3 ? WIN : (MODE == 2 ? 3 * WIN : (MODE == 5 ? 2 * WIN : WIN));
+    for (int i = threadIdx.x; i < (MODE == 3 ? 2 * WIN : n); i += blockDim.x) a32[i] = 0;
+    __syncthreads();
+    unsigned s = threadIdx.x * 2654435761u + blockIdx.x * 40503u + 1u;
+    for (int it = 0; it < iters; it++) {
+        s = s * 1664525u + 1013904223u;
+        int c = (int)((s >> 8) % WIN);
+        if (skew) {  // hot columns: c = WIN * u^3
+            const float u = (float)(s >> 8) * (1.0f / 16777216.0f);
+            c = min(WIN - 1, (int)(WIN * u * u * u));
+        }
+        if (MODE == 0) atomicAdd(&a32[c], 1);                          // one native ATOMS.ADD
+        if (MODE == 1) atomicOr((unsigned *)&a32[c >> 5 << 0], 1u << (c & 31));
+        if (MODE == 2) { atomicAdd(&a32[c], (int)(s & 16383)); atomicAdd(&a32[WIN + c], (int)((s >> 3) & 16383)); atomicAdd(&a32[2 * WIN + c], (int)(s >> 20)); }
+        if (MODE == 5) {  // 64-bit fixed point from two native 32-bit atomics: low word with carry-out, then high word
+            const unsigned lo = s * 2246822519u, hi = s >> 12;
+            const unsigned old = atomicAdd((unsigned *)&a32[c], lo);
+            atomicAdd((unsigned *)&a32[WIN + c], hi + ((old + lo) < old ? 1u : 0u));
+        }
+        if (MODE == 3) atomicAdd(&a64[c], 1.0);                        // CAS loop
+        if (MODE == 4) { double v = a64[c]; a64[c] = v + 1.0; }        // plain RMW (racy; throughput reference)
+    }
+    __syncthreads();
+    unsigned long long t = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t += (unsigned)a32[i];
+    if (t == 0xdeadbeefULL) sink[0] = t;
+}
+template <int MODE> void run(const char *name, size_t smem, int per, int skew = 0)
+{
+    cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    unsigned long long *sink; cudaMalloc(&sink, 8);
+    const int iters = 20000, grid = 148;
+    k<MODE><<<grid, 512, smem>>>(100, sink, skew);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0); k<MODE><<<grid, 512, smem>>>(iters, sink, skew); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double upd = (double)grid * 512 * iters;
+    printf("%-34s %8.3f ms  %7.1f G updates/s  %5.2f updates/clk/SM (x%d atomics each)  err=%s\n", name, ms, upd / ms / 1e6,
+           upd / grid / (ms * 1e-3 * 1.965e9), per, cudaGetErrorString(cudaGetLastError()));
+}
+int main()
+{
+    run<0>("int32 ATOMS.ADD", WIN * 4, 1);
+    run<1>("atomicOr 32", WIN * 4, 1);
+    run<5>("2 x ATOMS.ADD with carry (fixed64)", 2 * WIN * 4, 2);
+    run<5>("fixed64, hot columns (u^3)", 2 * WIN * 4, 2, 1);
+    run<0>("int32 ATOMS.ADD, hot columns", WIN * 4, 1, 1);
+    run<3>("f64 CAS, hot columns", WIN * 8, 1, 1);
+    run<4>("f64 plain RMW, hot columns", WIN * 8, 1, 1);
+    run<3>("f64 atomicAdd (CAS loop)", WIN * 8, 1);
+    run<4>("f64 plain LDS+DADD+STS (racy ref)", WIN * 8, 1);
+    return 0;
+}
