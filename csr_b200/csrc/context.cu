@@ -382,6 +382,9 @@ int csrk_set_option(const char *name, int64_t value)
         options().radix_bits = value;
     } else if (!strcmp(name, "spmv_zero_copy_y")) {
         options().spmv_zero_copy_y = value ? 1 : 0;
+    } else if (!strcmp(name, "fix_threads")) {
+        CSRK_ARG(value == 512 || value == 768 || value == 1024, "fix_threads must be 512, 768 or 1024");
+        options().fix_threads = value;
     } else if (!strcmp(name, "spgemm_fixed")) {
         options().spgemm_fixed = value ? 1 : 0;
     } else if (!strcmp(name, "own_chunk_prod")) {

@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(THREADS) k_num_dense(MatView A, MatView B, con
 constexpr int OWN_NW = 16, OWN_DEPTH = 16;
 constexpr int OWN_MAX_CHUNKS = 64;      // slices of one heavy row (A entries) handed to different CTAs
 constexpr int DENSE_THREADS = 512;
-constexpr int DENSE_WIN = 27648;                      // max columns per shared-memory accumulator window (216 KB)
+constexpr int DENSE_WIN = 26624;                      // max columns per shared-memory accumulator window (208 KB)
 constexpr int DENSE_MAX_PASSES = 4;                   // beyond that: global scratch, one pass
 
 __global__ void k_col_hist(const int32_t *__restrict__ ci, int64_t nnz, int *__restrict__ cnt)
@@ -1028,6 +1028,7 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
             int nitems, long long *__restrict__ partial, int e0)
 {
     static_assert(THREADS * 2 * 32 >= DENSE_WIN, "two bitmap words per thread must cover a window");
+    static_assert(THREADS % 32 == 0 && THREADS <= 1024, "whole warps");
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_idx, s_ri;
     __shared__ int s_next[FIX_MAX_PASSES];
@@ -1077,7 +1078,7 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
         const unsigned *kept = keep + (size_t)keep_slot[row] * n_words;
         int64_t out = c_rp[row];
         // batches of A entries are handed to the warps dynamically (pieces differ a lot in length)
-        const int bsz = (int)max((int64_t)1, min((int64_t)32, (ae - as + 2 * NWARP - 1) / (2 * NWARP)));
+        const int bsz = (int)max((int64_t)1, min((int64_t)32, (ae - as + 4 * NWARP - 1) / (4 * NWARP)));
         const int nbatch = (int)((ae - as + bsz - 1) / bsz);
         for (int q = 0; q < passes; q++) {
             const int c0 = q * win, c1 = min(c0 + win, n_cols);
@@ -1131,6 +1132,14 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
                     for (int u = 0; u < 4; u++) {
                         col[u] = ncol[u];
                         val[u] = nval[u];
+                    }
+                    if (t + 3 < cnt) {  // pull piece t+3 into L2 (no registers held)
+                        const int64_t fbs = __shfl_sync(0xffffffffu, bs, t + 3);
+                        const int flen = __shfl_sync(0xffffffffu, len, t + 3);
+                        if (lane * 32 < flen)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.ci + fbs + lane * 32));
+                        if (B.vk && lane * (128 / B.vk) < flen)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)B.vs + (fbs + lane * (128 / B.vk)) * B.vk));
                     }
                     if (t + 1 < cnt) {
                         nbs = __shfl_sync(0xffffffffu, bs, t + 1);
@@ -1186,14 +1195,16 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
             }
             // sweep: one thread per COLUMN, so that a warp writes consecutive output slots; the slot of
             // a column = kept bits below it (per-word prefix from a block scan + popcount inside the word)
-            int tot0, tot1;
+            int tot0, tot1 = 0;
             const int ex0 = block_exclusive_scan<int>(__popc(kb0), s_wt, tot0);
-            __syncthreads();
-            const int ex1 = block_exclusive_scan<int>(__popc(kb1), s_wt, tot1);
             s_bits[tid] = kb0;
-            s_bits[THREADS + tid] = kb1;
             s_wpre[tid] = ex0;
-            s_wpre[THREADS + tid] = tot0 + ex1;
+            if (THREADS * 32 < DENSE_WIN) {  // a second word per thread only for the smaller CTAs
+                __syncthreads();
+                const int ex1 = block_exclusive_scan<int>(__popc(kb1), s_wt, tot1);
+                s_bits[THREADS + tid] = kb1;
+                s_wpre[THREADS + tid] = tot0 + ex1;
+            }
             __syncthreads();
             for (int col = tid; col < c1 - c0; col += THREADS) {
                 const unsigned bits = s_bits[col >> 5];
@@ -1201,8 +1212,8 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
                 if (bits & bit) {
                     const int64_t o = out + s_wpre[col >> 5] + __popc(bits & (bit - 1u));
                     const long long v = (long long)(((unsigned long long)shi[col] << 32) | slo[col]);
-                    c_ci[o] = c0 + col;
-                    c_vs[o] = (double)v * inv_scale;
+                    __stcs(&c_ci[o], c0 + col);  // streaming: the 12 B/entry result must not evict B from L2
+                    __stcs(&c_vs[o], (double)v * inv_scale);
                     slo[col] = 0u;
                     shi[col] = 0u;
                 }
@@ -1608,11 +1619,26 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                 const int64_t ncomb = tots[2];  // chunked rows sit at the head of the LPT-ordered list
                 CSRK_TRACE_MARK("spgemm: light bins + dense prep (value range, bounds, split, items)", s);
                 if (fixed) {
-                    auto k = k_num_fixed<DENSE_THREADS>;
-                    CSRK_TRY(optin_smem(k, bytes));
-                    CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
-                                (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
-                                chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                    const int64_t ft = options().fix_threads.load();
+                    if (ft == 1024) {
+                        auto k = k_num_fixed<1024>;
+                        CSRK_TRY(optin_smem(k, bytes));
+                        CSRK_LAUNCH(k, (unsigned)grid, 1024, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                                    (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
+                                    chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                    } else if (ft == 768) {
+                        auto k = k_num_fixed<768>;
+                        CSRK_TRY(optin_smem(k, bytes));
+                        CSRK_LAUNCH(k, (unsigned)grid, 768, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                                    (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
+                                    chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                    } else {
+                        auto k = k_num_fixed<512>;
+                        CSRK_TRY(optin_smem(k, bytes));
+                        CSRK_LAUNCH(k, (unsigned)grid, 512, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                                    (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
+                                    chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                    }
                     if (nparts) {
                         CSRK_TRACE_MARK("spgemm: numeric (fixed-point kernel)", s);
                         CSRK_LAUNCH(k_fix_combine, (unsigned)(ncomb * passes), 256, 0, s, A, NL + noff[5], ncnt[5],

@@ -65,6 +65,7 @@ int csrk_synchronize(void);
  * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan;
  * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
  * "spmv_zero_copy_y" 1 | 0: csrk_spmv stores finished rows straight into y when y is pinned host memory;
+ * "fix_threads" 512 | 768 | 1024 threads per CTA of that kernel (default 1024);
  * "spgemm_fixed" 1 | 0: allow the fixed-point numeric kernel for heavy rows (see csrk_spgemm_path);
  * "own_chunk_prod" SpGEMM: rows with more products than this are cut into chunks of A entries handled by
  *               different CTAs and summed in chunk order (0 = 1/8 of an SM's fair share, < 0 = never:

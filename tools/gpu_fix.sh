@@ -1,5 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-echo "== full"; CSRK_TRACE=1 timeout 600 python tools/exp_block.py 1 0 2>&1 | grep -E "spgemm: numeric|products \+ symbolic|^rank" | tail -4
-echo "== blocks of 8"; timeout 600 python tools/exp_block.py 8 0,1,7 2>&1 | grep "^rank"
-echo "== fixed test (one)"; timeout 1200 python -m pytest tests -m gpu -q -x -k "fixed_point_path and f8" 2>&1 | tail -3
+mkdir -p gpurun_out
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_num_fixed -c 1 -f -o gpurun_out/fixed_full \
+    python tools/exp_spgemm.py 1.0 1 > gpurun_out/ncu_fx.log 2>&1; tail -1 gpurun_out/ncu_fx.log | cut -c1-80
