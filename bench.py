@@ -354,7 +354,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4),
                      "traffic": args.traffic if args.traffic is not None else (
-                         816282368 if (args.scale == 1.0 and args.col_skew == 1.0 and world == 1) else None),
+                         815749888 if (args.scale == 1.0 and args.col_skew == 1.0 and world == 1) else None),
                      "traffic_source": "profiles/r01_spmv_tile_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum per launch",
                      "peak_source": peak_src,
                      "kernel": "k_spmv_tile<int,float,float> (+k_spmv_fixup, 4% of the step)", "kernel_ms": round(ms_kernel, 5),
