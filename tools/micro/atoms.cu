@@ -1,3 +1,4 @@
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/atoms tools/micro/atoms.cu ; run on the GPU box.
 // Microbenchmark: shared-memory atomic throughput on B200 (random addresses in a 25k-entry window).
 #include <cstdio>
 #include <cstdint>
