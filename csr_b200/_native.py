@@ -47,6 +47,7 @@ SIGNATURES = {
     "csrk_spgemm_abt": (_int, [_vp, _vp, _P(_vp)]),
     "csrk_spgemm_stats": (_int, [_vp, _P(_i64), _P(_i64)]),
     "csrk_spgemm_path": (_int, [_vp, _P(_int)]),
+    "csrk_normalize_rows": (_int, [_vp, _int, _vp, _vp]),
     "csrk_transpose": (_int, [_vp, _int, _P(_vp)]),
     "csrk_order_columns": (_int, [_vp]),
     "csrk_filter_zeros": (_int, [_vp]),

@@ -373,6 +373,33 @@ class CSR:
                     svs.append(K.mult_vec(h, v))
             return np.concatenate(svs)
 
+    def normalize_rows(self, normalization):
+        """Normalise the rows in place and return the per-row means (``'center'``) or norms (``'unit'``)
+        (csr.py:443-469 -> transform.py:13-66), computed on the device.  Missing entries are ignored,
+        not treated as 0; an all-zero row under ``'unit'`` becomes NaN, as in the reference."""
+        if normalization not in ('center', 'unit'):
+            raise ValueError('unknown normalization: ' + normalization)
+        if self._values is None:
+            raise ValueError('normalize_rows needs a matrix with values')
+        K = get_kernel()
+        vs = np.ascontiguousarray(self._values)
+        if self.nnz <= K.max_nnz:
+            if self._resident:
+                vec = K.normalize_rows(_cache.get(self, K), normalization, values_out=vs)
+            else:
+                with releasing(K.to_handle(self), K) as h:
+                    vec = K.normalize_rows(h, normalization, values_out=vs)
+        else:   # rows are independent: normalise shard by shard (csr.py:599-621)
+            parts, at = [], 0
+            for s in self._shard_rows(K.max_nnz):
+                with releasing(K.to_handle(s), K) as h:
+                    parts.append(K.normalize_rows(h, normalization, values_out=vs[at:at + s.nnz]))
+                at += s.nnz
+            vec = np.concatenate(parts)
+        if vs is not self._values:
+            self._values[...] = vs
+        return vec
+
     def _shard_rows(self, tgt_nnz):
         "csr.py:599-621: split by rows so that every shard has at most tgt_nnz entries."
         assert tgt_nnz > 0

@@ -694,6 +694,27 @@ int csrk_order_columns(csrk_h h)
     return order_columns_run(h, ctx().stream);
 }
 
+int csrk_normalize_rows(csrk_h h, int kind, void *vec, void *values_out)
+{
+    CSRK_ARG(h != nullptr, "NULL handle");
+    CSRK_ARG(kind == 0 || kind == 1, "kind must be 0 (center) or 1 (unit), got %d", kind);
+    CSRK_ARG(h->val_kind == 4 || h->val_kind == 8, "normalize_rows needs a matrix with values");
+    CSRK_ARG(h->nrows == 0 || vec != nullptr, "output vector is NULL");
+    CSRK_TRY(ensure_init());
+    WsScope scope;
+    cudaStream_t s = ctx().stream;
+    DevBuf dvec;
+    const size_t bytes = (size_t)h->nrows * (size_t)h->val_kind;
+    CSRK_TRY(dvec.alloc(bytes ? bytes : 8, s));
+    CSRK_TRY(normalize_rows_run(h, kind, dvec.p, s));
+    if (bytes)
+        CSRK_CUDA(cudaMemcpyAsync(vec, dvec.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (values_out && h->nnz)
+        CSRK_CUDA(cudaMemcpyAsync(values_out, h->vs, (size_t)h->nnz * h->val_kind, cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    return CSRK_OK;
+}
+
 int csrk_filter_zeros(csrk_h h)
 {
     CSRK_ARG(h != nullptr, "NULL handle");

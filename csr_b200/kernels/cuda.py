@@ -204,6 +204,28 @@ def filter_zeros(h: cuda_h) -> None:
     h.nnz = nnz.value
 
 
+def normalize_rows(h: cuda_h, normalization: str, values_out=None) -> np.ndarray:
+    """Normalise the rows of the handle's matrix in place on the device and return the per-row
+    means ('center') or norms ('unit') in the values' dtype (csr/transform.py:13-66).
+    ``values_out`` (optional, C-contiguous array of nnz elements of the values' dtype) receives the
+    normalised values."""
+    kinds = {"center": 0, "unit": 1}
+    if normalization not in kinds:
+        raise ValueError('unknown normalization: ' + normalization)
+    raw = _live(h)
+    vk = C.c_int()
+    N.check(N.lib().csrk_dims(raw, None, None, None, None, C.byref(vk)), "dims")
+    if vk.value not in (4, 8):
+        raise ValueError("normalize_rows needs a matrix with values")
+    dt = np.float32 if vk.value == 4 else np.float64
+    vec = np.zeros(h.nrows, dt)
+    if values_out is not None and (values_out.dtype != dt or values_out.shape != (h.nnz,)
+                                   or not values_out.flags.c_contiguous):
+        raise ValueError("values_out must be a C-contiguous array of nnz elements of the matrix's value type")
+    N.check(N.lib().csrk_normalize_rows(raw, kinds[normalization], _ptr(vec), _ptr(values_out)), "normalize_rows")
+    return vec
+
+
 def subset_rows(h: cuda_h, begin: int, end: int) -> cuda_h:
     """Rows [begin, end) as a new handle (csr/structure.py:70-81), copied on the device."""
     out = C.c_void_p()

@@ -152,6 +152,14 @@ int csrk_transpose(csrk_h a, int with_values, csrk_h *at);
  * columns keep their relative order (the bubble sort is stable). */
 int csrk_order_columns(csrk_h h);
 
+/* ---- normalize_rows: csr/csr.py:443-469 -> csr/transform.py:13-66 ----------
+ * In place on the handle's values.  kind 0 = 'center' (subtract each non-empty row's mean, returns the
+ * means), kind 1 = 'unit' (power-of-two pre-normalisation, divide by the Euclidean norm, returns the
+ * norms; an all-zero row becomes NaN as in the reference).  vec: HOST array of nrows elements of the
+ * matrix's value type.  values_out (optional): HOST array of nnz elements that receives the normalised
+ * values (what the reference leaves in csr.values).  A matrix without values is an argument error. */
+int csrk_normalize_rows(csrk_h h, int kind, void *vec, void *values_out);
+
 /* ---- _filter_zeros: csr/_struct.py:61-79 ----------------------------------
  * In-place removal of stored zeros (no-op for value-less matrices). */
 int csrk_filter_zeros(csrk_h h);

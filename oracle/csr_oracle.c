@@ -30,6 +30,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 typedef int32_t i32;
 typedef int64_t i64;
@@ -466,5 +467,98 @@ int orc_filter_zeros(i32 nrows, void *rp, int rp_is64, i32 *ci, void *vs, int va
     if (rp_is64) ((i64 *)rp)[nrows] = nnz;
     else ((i32 *)rp)[nrows] = (i32)nnz;
     *new_nnz = nnz;
+    return ORC_OK;
+}
+
+/* ----------------------------------------------------------- normalisation */
+/* csr/transform.py:13-26 (center_rows): per non-empty row, m = mean of the stored values, subtracted in
+ * place; returns the means in the values' dtype.  numba's np.mean accumulates sequentially in the ARRAY's
+ * dtype and divides by the (int64) size, which promotes to float64; `values -= m` is evaluated in
+ * float64 and stored back in the array's dtype. */
+int orc_center_rows(i32 nrows, const void *rp, int rp_is64, void *vs, int val_kind, void *means)
+{
+    if (val_kind != 4 && val_kind != 8)
+        return ORC_EARG;
+    for (i32 i = 0; i < nrows; i++) {
+        i64 sp = rp_is64 ? ((const i64 *)rp)[i] : ((const i32 *)rp)[i];
+        i64 ep = rp_is64 ? ((const i64 *)rp)[i + 1] : ((const i32 *)rp)[i + 1];
+        if (val_kind == 4) ((float *)means)[i] = 0.0f;
+        else ((double *)means)[i] = 0.0;
+        if (sp == ep)
+            continue;
+        if (val_kind == 4) {
+            float *v = (float *)vs;
+            float c = 0.0f;
+            for (i64 k = sp; k < ep; k++)
+                c += v[k];
+            double m = (double)c / (double)(ep - sp);
+            ((float *)means)[i] = (float)m;
+            for (i64 k = sp; k < ep; k++)
+                v[k] = (float)((double)v[k] - m);
+        } else {
+            double *v = (double *)vs;
+            double c = 0.0;
+            for (i64 k = sp; k < ep; k++)
+                c += v[k];
+            double m = c / (double)(ep - sp);
+            ((double *)means)[i] = m;
+            for (i64 k = sp; k < ep; k++)
+                v[k] -= m;
+        }
+    }
+    return ORC_OK;
+}
+
+/* csr/transform.py:29-66 (unit_rows): pre-normalise by a power of two taken from the largest magnitude
+ * (so that tiny rows do not underflow when squared), Euclidean norm, divide.  The reference's norm is
+ * BLAS nrm2 (np.linalg.norm under numba); here it is sqrt of a float64 sum of squares, so norms agree to
+ * a few ulp, not bit for bit -- tests state the tolerance. */
+int orc_unit_rows(i32 nrows, const void *rp, int rp_is64, void *vs, int val_kind, void *norms)
+{
+    if (val_kind != 4 && val_kind != 8)
+        return ORC_EARG;
+    const int maxexp = val_kind == 4 ? 128 : 1024, minexp = val_kind == 4 ? -126 : -1022; /* np.finfo */
+    for (i32 i = 0; i < nrows; i++) {
+        i64 sp = rp_is64 ? ((const i64 *)rp)[i] : ((const i32 *)rp)[i];
+        i64 ep = rp_is64 ? ((const i64 *)rp)[i + 1] : ((const i32 *)rp)[i + 1];
+        if (val_kind == 4) ((float *)norms)[i] = 0.0f;
+        else ((double *)norms)[i] = 0.0;
+        if (sp == ep)
+            continue;
+        double vmax = 0.0;
+        for (i64 k = sp; k < ep; k++) {
+            double a = fabs(val_kind == 4 ? (double)((float *)vs)[k] : ((double *)vs)[k]);
+            if (a > vmax || a != a)
+                vmax = a;
+        }
+        int ve = 0;
+        (void)frexp(vmax, &ve);
+        int pnexp = -ve < maxexp - 1 ? -ve : maxexp - 1;
+        if (pnexp < minexp)
+            pnexp = minexp;
+        const double prenorm = ldexp(1.0, pnexp);
+        double ss = 0.0;
+        if (val_kind == 4) {
+            float *v = (float *)vs;
+            for (i64 k = sp; k < ep; k++) {
+                v[k] = (float)((double)v[k] * prenorm);
+                ss += (double)v[k] * (double)v[k];
+            }
+            const float inorm = (float)sqrt(ss);
+            ((float *)norms)[i] = (float)((double)inorm / prenorm);
+            for (i64 k = sp; k < ep; k++)
+                v[k] = v[k] / inorm;
+        } else {
+            double *v = (double *)vs;
+            for (i64 k = sp; k < ep; k++) {
+                v[k] = v[k] * prenorm;
+                ss += v[k] * v[k];
+            }
+            const double inorm = sqrt(ss);
+            ((double *)norms)[i] = inorm / prenorm;
+            for (i64 k = sp; k < ep; k++)
+                v[k] = v[k] / inorm;
+        }
+    }
     return ORC_OK;
 }

@@ -52,10 +52,12 @@ def lib():
         L.orc_transpose.argtypes = [i32, i32, i64, vp, ip, vp, vp, ip, vp, vp, vp]
         L.orc_sort_rows.argtypes = [i32, vp, ip, vp, vp, ip]
         L.orc_filter_zeros.argtypes = [i32, vp, ip, vp, vp, ip, C.POINTER(i64)]
+        L.orc_center_rows.argtypes = [i32, vp, ip, vp, ip, vp]
+        L.orc_unit_rows.argtypes = [i32, vp, ip, vp, ip, vp]
         L.orc_free.argtypes = [vp]
         L.orc_free.restype = None
         for f in ("orc_mult_vec", "orc_mult_ab", "orc_mult_abt", "orc_sym_mm", "orc_transpose",
-                  "orc_sort_rows", "orc_filter_zeros"):
+                  "orc_sort_rows", "orc_filter_zeros", "orc_center_rows", "orc_unit_rows"):
             getattr(L, f).restype = C.c_int
         _lib = L
     return _lib
@@ -209,6 +211,20 @@ def filter_zeros(m) -> Mat:
     _check(rc, "filter_zeros")
     n = nnz.value
     return Mat(m.nrows, m.ncols, n, m.rowptrs, m.colinds[:n].copy(), m.values[:n].copy())
+
+
+def normalize_rows(m, normalization: str):
+    """csr/csr.py:443-469 -> csr/transform.py:13-66.  Returns (per-row vector, normalised COPY)."""
+    m = as_mat(m).copy()
+    if m.values is None:
+        raise ValueError("normalize_rows needs values")
+    vec = np.zeros(m.nrows, m.values.dtype)
+    fn = {"center": lib().orc_center_rows, "unit": lib().orc_unit_rows}.get(normalization)
+    if fn is None:
+        raise ValueError("unknown normalization: " + normalization)
+    _check(fn(m.nrows, _p(m.rowptrs), int(m.rowptrs.dtype.itemsize == 8), _p(m.values), _vk(m.values), _p(vec)),
+           "normalize_rows")
+    return vec, m
 
 
 def canonical(m: Mat) -> Mat:
