@@ -1,0 +1,63 @@
+"""
+GPU: nopython code driving the cuda kernel through csr_b200/kernels/cuda_numba.py:
+the same results as the object-mode kernel module, which the other GPU tests pin to the oracle.
+"""
+
+import numpy as np
+import pytest
+
+numba = pytest.importorskip("numba")
+from numba import njit  # noqa: E402
+
+from csr_b200 import synth  # noqa: E402
+from csr_b200.kernels import cuda_numba as cn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@njit
+def _power_step(h, x):
+    y = cn.mult_vec(h, x)
+    return y, np.sqrt((y * y).sum())
+
+
+@njit
+def _gram(h):
+    "A A^T from nopython: product, copy-out, release."
+    c = cn.mult_abt(h, h)
+    nr, nc, nnz, rp, ci, vs = cn.export_arrays(c)
+    cn.release_handle(c)
+    return nr, nc, nnz, rp, ci, vs
+
+
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
+def test_mult_vec_from_nopython(kernel, dtype):
+    A = synth.powerlaw_csr(5000, 3000, 200000, seed=31, dtype=dtype, alpha=1.0)
+    h = kernel.to_handle(A)
+    try:
+        for x in (synth.dense_vector(A.ncols, 1, "f8"), synth.dense_vector(A.ncols, 2, "f4"),
+                  np.arange(A.ncols, dtype=np.int64) % 7):
+            y, nrm = _power_step(h.H, x)
+            ref = kernel.mult_vec(h, x)
+            assert y.dtype == np.float64 and np.array_equal(y, ref)
+            assert nrm == pytest.approx(np.sqrt((ref * ref).sum()))
+        assert tuple(int(v) for v in cn.dims(h.H)) == (A.nrows, A.ncols, A.nnz, 0, A.values.dtype.itemsize)
+        with pytest.raises(ValueError):
+            _power_step(h.H, np.zeros(A.ncols + 1))
+    finally:
+        kernel.release_handle(h)
+
+
+def test_product_and_export_from_nopython(kernel):
+    A = synth.powerlaw_csr(2000, 1500, 60000, seed=37, dtype="f8", alpha=0.8)
+    h = kernel.to_handle(A)
+    try:
+        nr, nc, nnz, rp, ci, vs = _gram(h.H)
+        ch = kernel.mult_abt(h, h)
+        ref = kernel.from_handle(ch)
+        kernel.release_handle(ch)
+    finally:
+        kernel.release_handle(h)
+    assert (nr, nc, nnz) == (ref.nrows, ref.ncols, ref.nnz)
+    assert rp.dtype == np.int64 and np.array_equal(rp, ref.rowptrs) and np.array_equal(ci, ref.colinds)
+    assert np.allclose(vs, ref.values, rtol=1e-12, atol=0.0)
