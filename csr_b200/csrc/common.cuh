@@ -168,6 +168,8 @@ void matrix_destroy(csrk_matrix *m, cudaStream_t s);
 void plan_destroy(SpmvPlan *p, cudaStream_t s);
 void plan_invalidate(csrk_matrix *m, cudaStream_t s);
 int normalize_rows_run(csrk_matrix *h, int kind, void *d_vec, cudaStream_t s);
+int from_coo_run(int32_t nrows, int32_t ncols, int64_t nnz, const int32_t *d_rows, const int32_t *d_cols,
+                 const void *d_vals, int val_kind, csrk_matrix **out, cudaStream_t s);  // syncs internally
 void psf_destroy(PsfPlan *p, cudaStream_t s);
 int psf_build(csrk_matrix *h, int x_kind, PsfPlan **out, cudaStream_t s);  // syncs internally
 int psf_run(csrk_matrix *h, PsfPlan *p, const void *d_x, double *d_y, cudaStream_t s);

@@ -694,6 +694,36 @@ int csrk_order_columns(csrk_h h)
     return order_columns_run(h, ctx().stream);
 }
 
+int csrk_from_coo(int32_t nrows, int32_t ncols, int64_t nnz, const int32_t *rows, const int32_t *cols, const void *values,
+                  int val_kind, csrk_h *out)
+{
+    CSRK_ARG(out != nullptr, "out is NULL");
+    *out = nullptr;
+    CSRK_ARG(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative dimension");
+    CSRK_ARG(val_kind == 0 || val_kind == 4 || val_kind == 8, "val_kind must be 0, 4 or 8 (got %d)", val_kind);
+    CSRK_ARG(nnz == 0 || (rows != nullptr && cols != nullptr), "rows / cols is NULL");
+    CSRK_ARG(nnz == 0 || val_kind == 0 || values != nullptr, "values is NULL");
+    CSRK_ARG(nnz == 0 || (nrows > 0 && ncols > 0), "entries in an empty shape");
+    CSRK_TRY(ensure_init());
+    WsScope scope;
+    cudaStream_t s = ctx().stream;
+    DevBuf dr, dc, dv;
+    if (nnz) {
+        CSRK_TRY(dr.alloc((size_t)nnz * 4, s));
+        CSRK_TRY(dc.alloc((size_t)nnz * 4, s));
+        CSRK_CUDA(cudaMemcpyAsync(dr.p, rows, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+        CSRK_CUDA(cudaMemcpyAsync(dc.p, cols, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+        if (val_kind) {
+            CSRK_TRY(dv.alloc((size_t)nnz * val_kind, s));
+            CSRK_CUDA(cudaMemcpyAsync(dv.p, values, (size_t)nnz * val_kind, cudaMemcpyHostToDevice, s));
+        }
+    }
+    csrk_matrix *m = nullptr;
+    CSRK_TRY(from_coo_run(nrows, ncols, nnz, dr.as<int32_t>(), dc.as<int32_t>(), dv.p, val_kind, &m, s));
+    *out = m;
+    return CSRK_OK;
+}
+
 int csrk_normalize_rows(csrk_h h, int kind, void *vec, void *values_out)
 {
     CSRK_ARG(h != nullptr, "NULL handle");

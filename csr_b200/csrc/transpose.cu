@@ -284,4 +284,83 @@ int order_columns_run(csrk_matrix *h, cudaStream_t s)
     return order_typed<int32_t, NoPayload>(h, s);
 }
 
+// ---- from_coo (csr/structure.py:11-58): stable sort of the triples by row -----------------------
+// The reference counts per row and scatters with a per-row cursor, i.e. entries keep their COO
+// order inside a row.  Same machinery as the transpose with the roles swapped: key = row,
+// payloads = column and value; the rowptrs are read off the sorted keys.
+__global__ void k_range_flag(const int32_t *__restrict__ idx, int64_t n, int32_t bound, int *__restrict__ flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (idx[i] < 0 || idx[i] >= bound))
+        *flag = 1;
+}
+
+template <typename RPT, typename VT>
+static int from_coo_typed(csrk_matrix *m, const int32_t *d_rows, const int32_t *d_cols, const VT *d_vals, cudaStream_t s)
+{
+    constexpr bool HASV = !std::is_same<VT, NoPayload>::value;
+    DevBuf skeys;
+    CSRK_TRY(skeys.alloc(sizeof(int32_t) * (size_t)m->nnz, s));
+    CSRK_TRY((radix_sort_by_key<VT>(d_rows, d_cols, d_vals, m->nnz, key_bits(m->nrows), m->ci,
+                                    HASV ? (VT *)m->vs : nullptr, s, skeys.as<int32_t>())));
+    CSRK_LAUNCH((k_key_bounds<RPT>), (unsigned)div_up(div_up(m->nnz + 1, 4), 256), 256, 0, s, skeys.as<int32_t>(), m->nnz,
+                m->nrows, (RPT *)m->rp);
+    return CSRK_OK;
+}
+
+// d_rows/d_cols: int32[nnz] on the device, d_vals: val_kind-typed or null.  Indices outside the shape
+// are an argument error (the reference asserts them on the host, csr/csr.py:152-159).
+int from_coo_run(int32_t nrows, int32_t ncols, int64_t nnz, const int32_t *d_rows, const int32_t *d_cols,
+                 const void *d_vals, int val_kind, csrk_matrix **out, cudaStream_t s)
+{
+    *out = nullptr;
+    const int rp_is64 = nnz > (int64_t)INT32_MAX ? 1 : 0;  // csr/csr.py:90-93
+    csrk_matrix *m = nullptr;
+    CSRK_TRY(matrix_alloc(&m, nrows, ncols, nnz, rp_is64, val_kind, s));
+    auto fail = [&](int rc) {
+        matrix_destroy(m, s);
+        return rc;
+    };
+    int rc = CSRK_OK;
+    if (nnz == 0) {
+        cudaError_t e = cudaMemsetAsync(m->rp, 0, ((size_t)nrows + 1) * (rp_is64 ? 8 : 4), s);
+        if (e != cudaSuccess)
+            return fail(cuda_fail(e, "from_coo", __FILE__, __LINE__));
+    } else {
+        DevBuf flag;
+        rc = flag.alloc_zero(sizeof(int), s);
+        if (rc != CSRK_OK)
+            return fail(rc);
+        k_range_flag<<<(unsigned)div_up(nnz, 256), 256, 0, s>>>(d_rows, nnz, nrows, flag.as<int>());
+        k_range_flag<<<(unsigned)div_up(nnz, 256), 256, 0, s>>>(d_cols, nnz, ncols, flag.as<int>());
+        g_launches.fetch_add(2);
+        int bad = 0;
+        cudaError_t e = cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess)
+            return fail(cuda_fail(e, "from_coo", __FILE__, __LINE__));
+        if (bad) {
+            set_error("from_coo: a row or column index is outside the shape %d x %d", nrows, ncols);
+            return fail(CSRK_EARG);
+        }
+        if (rp_is64) {
+            if (val_kind == 4) rc = from_coo_typed<int64_t, float>(m, d_rows, d_cols, (const float *)d_vals, s);
+            else if (val_kind == 8) rc = from_coo_typed<int64_t, double>(m, d_rows, d_cols, (const double *)d_vals, s);
+            else rc = from_coo_typed<int64_t, NoPayload>(m, d_rows, d_cols, (const NoPayload *)nullptr, s);
+        } else {
+            if (val_kind == 4) rc = from_coo_typed<int32_t, float>(m, d_rows, d_cols, (const float *)d_vals, s);
+            else if (val_kind == 8) rc = from_coo_typed<int32_t, double>(m, d_rows, d_cols, (const double *)d_vals, s);
+            else rc = from_coo_typed<int32_t, NoPayload>(m, d_rows, d_cols, (const NoPayload *)nullptr, s);
+        }
+        if (rc != CSRK_OK)
+            return fail(rc);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+        return fail(cuda_fail(e, "from_coo", __FILE__, __LINE__));
+    *out = m;
+    return CSRK_OK;
+}
+
 }  // namespace csrk

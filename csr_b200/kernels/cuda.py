@@ -204,6 +204,33 @@ def filter_zeros(h: cuda_h) -> None:
     h.nnz = nnz.value
 
 
+def from_coo(rows, cols, vals, shape=None, csr_cls=None) -> cuda_h:
+    """COO triples -> a resident handle, sorted by row on the device with the COO order kept inside
+    each row (csr/csr.py:140-169 -> csr/structure.py:11-58).  ``from_handle`` gives the host CSR."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    assert np.min(rows, initial=0) >= 0
+    assert np.min(cols, initial=0) >= 0
+    if shape is not None:
+        nrows, ncols = (int(v) for v in shape)
+        assert np.max(rows, initial=0) < max(nrows, 1)
+        assert np.max(cols, initial=0) < max(ncols, 1)
+    else:
+        nrows = int(np.max(rows)) + 1
+        ncols = int(np.max(cols)) + 1
+    nnz = len(rows)
+    assert len(cols) == nnz
+    assert vals is None or len(vals) == nnz
+    if vals is not None:
+        vals = np.ascontiguousarray(vals)
+        if vals.dtype != np.float32:
+            vals = vals.astype(np.float64, copy=False)
+    out = C.c_void_p()
+    N.check(N.lib().csrk_from_coo(nrows, ncols, nnz, _ptr(rows), _ptr(cols), _ptr(vals),
+                                  0 if vals is None else vals.dtype.itemsize, C.byref(out)), "from_coo")
+    return _wrap(out, csr_cls)
+
+
 def normalize_rows(h: cuda_h, normalization: str, values_out=None) -> np.ndarray:
     """Normalise the rows of the handle's matrix in place on the device and return the per-row
     means ('center') or norms ('unit') in the values' dtype (csr/transform.py:13-66).

@@ -152,6 +152,13 @@ int csrk_transpose(csrk_h a, int with_values, csrk_h *at);
  * columns keep their relative order (the bubble sort is stable). */
 int csrk_order_columns(csrk_h h);
 
+/* ---- from_coo: csr/csr.py:140-169 -> csr/structure.py:11-58 -----------------
+ * Build a handle straight from COO triples on the host (int32 rows/cols, values of val_kind 0|4|8):
+ * entries keep their COO order inside a row (stable), values keep their dtype, rowptrs are int32
+ * unless nnz > INT32_MAX.  An index outside the shape is CSRK_EARG. */
+int csrk_from_coo(int32_t nrows, int32_t ncols, int64_t nnz, const int32_t *rows, const int32_t *cols, const void *values,
+                  int val_kind, csrk_h *out);
+
 /* ---- normalize_rows: csr/csr.py:443-469 -> csr/transform.py:13-66 ----------
  * In place on the handle's values.  kind 0 = 'center' (subtract each non-empty row's mean, returns the
  * means), kind 1 = 'unit' (power-of-two pre-normalisation, divide by the Euclidean norm, returns the

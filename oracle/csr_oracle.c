@@ -562,3 +562,35 @@ int orc_unit_rows(i32 nrows, const void *rp, int rp_is64, void *vs, int val_kind
     }
     return ORC_OK;
 }
+
+/* ---------------------------------------------------------------- from_coo */
+/* csr/structure.py:11-58 (_from_coo_structure / _from_coo_values): count per row, prefix sum,
+ * stable scatter with a per-row cursor -- entries keep their COO order inside a row; values keep
+ * their dtype.  rowptrs are int64 here; the CSR constructor narrows them (csr/csr.py:90-93). */
+int orc_from_coo(i32 nrows, i64 nnz, const i32 *rows, const i32 *cols, const void *vals, int val_kind,
+                 i64 *rowptrs, i32 *out_cols, void *out_vals)
+{
+    i64 *rpos = (i64 *)calloc((size_t)nrows + 1, sizeof(i64));
+    if (!rpos)
+        return ORC_ENOMEM;
+    for (i32 i = 0; i <= nrows; i++)
+        rowptrs[i] = 0;
+    for (i64 k = 0; k < nnz; k++) {
+        if (rows[k] < 0 || rows[k] >= nrows) {
+            free(rpos);
+            return ORC_EARG;
+        }
+        rowptrs[rows[k] + 1]++;
+    }
+    for (i32 i = 0; i < nrows; i++)
+        rowptrs[i + 1] += rowptrs[i];
+    memcpy(rpos, rowptrs, ((size_t)nrows + 1) * sizeof(i64));
+    for (i64 k = 0; k < nnz; k++) {
+        const i64 pos = rpos[rows[k]]++;
+        out_cols[pos] = cols[k];
+        if (val_kind == 4) ((float *)out_vals)[pos] = ((const float *)vals)[k];
+        else if (val_kind == 8) ((double *)out_vals)[pos] = ((const double *)vals)[k];
+    }
+    free(rpos);
+    return ORC_OK;
+}

@@ -54,10 +54,11 @@ def lib():
         L.orc_filter_zeros.argtypes = [i32, vp, ip, vp, vp, ip, C.POINTER(i64)]
         L.orc_center_rows.argtypes = [i32, vp, ip, vp, ip, vp]
         L.orc_unit_rows.argtypes = [i32, vp, ip, vp, ip, vp]
+        L.orc_from_coo.argtypes = [i32, i64, vp, vp, vp, ip, vp, vp, vp]
         L.orc_free.argtypes = [vp]
         L.orc_free.restype = None
         for f in ("orc_mult_vec", "orc_mult_ab", "orc_mult_abt", "orc_sym_mm", "orc_transpose",
-                  "orc_sort_rows", "orc_filter_zeros", "orc_center_rows", "orc_unit_rows"):
+                  "orc_sort_rows", "orc_filter_zeros", "orc_center_rows", "orc_unit_rows", "orc_from_coo"):
             getattr(L, f).restype = C.c_int
         _lib = L
     return _lib
@@ -225,6 +226,26 @@ def normalize_rows(m, normalization: str):
     _check(fn(m.nrows, _p(m.rowptrs), int(m.rowptrs.dtype.itemsize == 8), _p(m.values), _vk(m.values), _p(vec)),
            "normalize_rows")
     return vec, m
+
+
+def from_coo(rows, cols, vals, shape) -> Mat:
+    """csr/csr.py:140-169 -> csr/structure.py:11-58 (shape given; rowptr dtype by the rule of csr.py:90-93)."""
+    nrows, ncols = (int(v) for v in shape)
+    rows = np.ascontiguousarray(rows, np.int32)
+    cols = np.ascontiguousarray(cols, np.int32)
+    nnz = len(rows)
+    assert len(cols) == nnz and (vals is None or len(vals) == nnz)
+    if vals is not None:
+        vals = np.ascontiguousarray(vals)
+        if vals.dtype != np.float32:
+            vals = vals.astype(np.float64)
+    rp = np.zeros(nrows + 1, np.int64)
+    oc = np.empty(nnz, np.int32)
+    ov = None if vals is None else np.empty_like(vals)
+    _check(lib().orc_from_coo(nrows, nnz, _p(rows), _p(cols), _p(vals), _vk(vals), _p(rp), _p(oc), _p(ov)), "from_coo")
+    if nnz <= np.iinfo(np.int32).max:
+        rp = rp.astype(np.int32)
+    return Mat(nrows, ncols, nnz, rp, oc, ov)
 
 
 def canonical(m: Mat) -> Mat:
