@@ -210,3 +210,23 @@ def test_package_exports():
     assert csr_b200.CSR is CSR
     for n in ('get_kernel', 'set_kernel', 'use_kernel', 'releasing'):
         assert hasattr(csr_b200, n)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: stdout carries ONE JSON line (library banners, logs -> stderr).  The reference arm
+    runs on the CPU (the oracle port of the numba kernel), so this is checkable without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--scale", "0.005"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "spmv_hbm_gbs" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
