@@ -252,15 +252,68 @@ class CSR:
         return self.values[sp:ep]
 
     def row(self, row):
-        "Dense copy of one row (csr/_rows.py:16-60, scalar index only)."
-        sp, ep = self.row_extent(row)
-        if self.values is None:
-            v = np.zeros(self.ncols, dtype=np.float32)
-            v[self.colinds[sp:ep]] = 1
-        else:
-            v = np.zeros(self.ncols, dtype=self.values.dtype)
-            v[self.colinds[sp:ep]] = self.values[sp:ep]
+        """Dense copy of one row, or a ``k x ncols`` matrix for an array of row indices
+        (csr/csr.py:373-387 -> csr/_rows.py:16-87)."""
+        row = np.asarray(row, dtype='i4')
+        dtype = np.float32 if self.values is None else self.values.dtype
+        return self._rows_dense(row, dtype, mask=False)
+
+    def row_mask(self, row):
+        "Dense logical array(s) marking the columns stored in the row(s) (csr/csr.py:389-404)."
+        return self._rows_dense(np.asarray(row, dtype='i4'), np.bool_, mask=True)
+
+    def _rows_dense(self, row, dtype, mask):
+        v = np.zeros(row.shape + (self.ncols,), dtype=dtype)
+        if self.nnz == 0:
+            return v
+        for i, r in enumerate(np.atleast_1d(row)):
+            sp, ep = self.row_extent(int(r))
+            tgt = v if row.shape == () else v[i, :]
+            tgt[self.colinds[sp:ep]] = 1 if (mask or self.values is None) else self.values[sp:ep]
         return v
+
+    def pick_rows(self, rows, *, include_values=True):
+        """The given rows (repeats allowed) as a new matrix with int32 rowptrs
+        (csr/csr.py:347-364 -> csr/structure.py:85-153)."""
+        rows = np.asarray(rows, dtype=np.int64)
+        lens = np.diff(self.rowptrs.astype(np.int64))[rows] if len(rows) else np.zeros(0, np.int64)
+        rp = np.zeros(len(rows) + 1, dtype=np.int32)
+        np.cumsum(lens, out=rp[1:])
+        nnz = int(rp[-1])
+        # position k of the result comes from rowptrs[rows[r]] + (k - rp[r])
+        src = np.repeat(self.rowptrs.astype(np.int64)[rows] - rp[:-1].astype(np.int64), lens) + np.arange(nnz, dtype=np.int64)
+        vals = self.values[src] if (include_values and self.values is not None) else None
+        return CSR(len(rows), self.ncols, nnz, rp, self.colinds[src].astype(np.int32, copy=False), vals)
+
+    def filter_nnzs(self, filt):
+        "Keep the entries where ``filt`` (length nnz) is true (csr/csr.py:494-522)."
+        filt = np.asarray(filt)
+        if len(filt) != self.nnz:
+            raise ValueError('filter has length %d, expected %d' % (len(filt), self.nnz))
+        keep = filt.astype(bool)
+        rps2 = np.zeros_like(self.rowptrs)
+        if self.nnz:
+            per_row = np.add.reduceat(np.concatenate([keep.astype(np.int64), [0]]),
+                                      np.minimum(self.rowptrs[:-1].astype(np.int64), self.nnz))
+            per_row[np.diff(self.rowptrs) == 0] = 0
+            np.cumsum(per_row, out=rps2[1:])
+        nnz2 = int(rps2[-1])
+        assert nnz2 == int(np.sum(keep))
+        vs = self.values
+        return CSR(self.nrows, self.ncols, nnz2, rps2, self.colinds[keep], None if vs is None else vs[keep])
+
+    def drop_values(self):
+        "Remove the value array in place (deprecated in the reference: csr/csr.py:652-661)."
+        import warnings
+        warnings.warn('drop_values is deprecated', DeprecationWarning)
+        self.values = None
+
+    def fill_values(self, value):
+        "Set every stored value in place; adds float64 values to a structure-only matrix (csr/csr.py:663-675)."
+        if self.values is not None:
+            self.values[:] = value
+        else:
+            self.values = np.full(self.nnz, value, dtype='float64')
 
     def row_nnzs(self):
         return np.diff(self.rowptrs)
