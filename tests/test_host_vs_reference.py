@@ -19,15 +19,20 @@ from csr_b200 import CSR  # noqa: E402
 
 @pytest.fixture(scope="module")
 def refmod():
-    os.environ.setdefault("CSR_KERNEL", "numba")
-    sys.dont_write_bytecode = True
-    saved = sys.path[:]
+    old_env, old_flag, saved = os.environ.get("CSR_KERNEL"), sys.dont_write_bytecode, sys.path[:]
+    os.environ["CSR_KERNEL"] = "numba"       # for the reference's import only; restored below
+    sys.dont_write_bytecode = True           # /root/reference is read-only
     sys.path.insert(0, REF)
     try:
         import csr as ref
-        yield ref
     finally:
         sys.path[:] = saved
+        sys.dont_write_bytecode = old_flag
+        if old_env is None:
+            os.environ.pop("CSR_KERNEL", None)
+        else:
+            os.environ["CSR_KERNEL"] = old_env
+    yield ref
 
 
 def pair(ref, seed, values=True, dtype="f8", nrows=40, ncols=30, nnz=300):
