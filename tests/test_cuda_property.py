@@ -225,3 +225,72 @@ def test_sharded_paths(kernel, data, lim):
     # atomics can differ between the two runs
     assert_values_close(sh.values, full.values, 1e-12, abs_product_scale(A, B))
     assert_values_close(ysh, yfull, 1e-12, float(np.abs(A.values).max(initial=0.0)) * A.ncols)
+
+
+@given(csrs(values=True))
+def test_mean_center(kernel, csr):
+    "tests/test_transform.py:88-125, on the device (CSR.normalize_rows -> csrk_normalize_rows)"
+    backup = csr.copy()
+    rel_tol, abs_tol = (1.0e-5, 1.0e-3) if csr.values.dtype == np.dtype('f4') else (1.0e-6, 1.0e-10)
+    m2 = csr.normalize_rows('center')
+    assert len(m2) == csr.nrows and m2.dtype == csr.values.dtype
+    rnnz = csr.row_nnzs()
+    for i in range(csr.nrows):
+        vs, b_vs, b_row = csr.row_vs(i), backup.row_vs(i), backup.row(i)
+        if rnnz[i] > 0:
+            assert m2[i] == approx(np.mean(b_vs), rel=rel_tol, abs=abs_tol)
+            assert m2[i] == approx(np.sum(b_row) / rnnz[i], rel=rel_tol, abs=abs_tol)
+            assert np.mean(vs) == approx(0.0, rel=rel_tol, abs=abs_tol)
+            assert vs + m2[i] == approx(b_row[csr.row_cs(i)], rel=rel_tol, abs=abs_tol)
+        else:
+            assert m2[i] == 0.0
+    # and the oracle, tighter
+    rvec, ref = orc.normalize_rows(backup, 'center')
+    rt = 1e-5 if csr.values.dtype == np.float32 else 1e-12
+    scale = float(np.abs(backup.values).max(initial=0.0))
+    assert np.all(np.abs(m2.astype(np.float64) - rvec) <= rt * (np.abs(rvec) + scale))
+    assert np.all(np.abs(csr.values.astype(np.float64) - ref.values) <= rt * (np.abs(ref.values) + scale))
+
+
+@given(csrs(values=True))
+def test_unit_norm(kernel, csr):
+    "tests/test_transform.py:128-147, on the device"
+    backup = csr.copy()
+    with np.errstate(all='ignore'):
+        m2 = csr.normalize_rows('unit')
+    assert len(m2) == csr.nrows and m2.dtype == csr.values.dtype
+    for i in range(csr.nrows):
+        vs, bvs = csr.row_vs(i), backup.row_vs(i)
+        if len(vs) > 0:
+            assert m2[i] == approx(np.linalg.norm(bvs))
+            if m2[i] > 0:
+                assert np.linalg.norm(vs) == approx(1.0)
+                assert vs * m2[i] == approx(backup.row_vs(i))
+            else:
+                assert all(np.isnan(vs))
+        else:
+            assert m2[i] == 0.0
+
+
+@given(st.data(), st.integers(1, 60), st.integers(1, 60), st.sampled_from(['f4', 'f8', None]))
+def test_from_coo_on_device(kernel, data, nrows, ncols, dtype):
+    "csr/csr.py:140-169: any COO order, duplicates allowed; bit-identical to the oracle's stable scatter"
+    n = data.draw(st.integers(0, 400))
+    rows = data.draw(nph.arrays(np.int32, n, elements=st.integers(0, nrows - 1)))
+    cols = data.draw(nph.arrays(np.int32, n, elements=st.integers(0, ncols - 1)))
+    vals = None if dtype is None else data.draw(finite_arrays(n, dtype=np.dtype(dtype)))
+    ref = orc.from_coo(rows, cols, vals, (nrows, ncols))
+    h = kernel.from_coo(rows, cols, vals, (nrows, ncols))
+    try:
+        got = kernel.from_handle(h)
+    finally:
+        kernel.release_handle(h)
+    assert got.rowptrs.dtype == ref.rowptrs.dtype and np.array_equal(got.rowptrs, ref.rowptrs)
+    assert np.array_equal(got.colinds, ref.colinds)
+    if dtype is None:
+        assert got.values is None
+    else:
+        assert got.values.dtype == ref.values.dtype and np.array_equal(got.values, ref.values)
+    # the host constructor builds the same matrix
+    hc = CSR.from_coo(rows, cols, vals, (nrows, ncols))
+    assert np.array_equal(hc.rowptrs, ref.rowptrs) and np.array_equal(hc.colinds, ref.colinds)
