@@ -39,6 +39,7 @@ SIGNATURES = {
     "csrk_device_ptrs": (_int, [_vp, _P(_vp), _P(_vp), _P(_vp)]),
     "csrk_subset_rows": (_int, [_vp, _i32, _i32, _P(_vp)]),
     "csrk_spmv": (_int, [_vp, _vp, _int, _vp]),
+    "csrk_spmv_plan_info": (_int, [_vp, _int, _P(_i64)]),
     "csrk_spmv_dev": (_int, [_vp, _vp, _int, _vp, _vp]),
     "csrk_spmv_dev_multi": (_int, [_vp, _vp, _int, _P(_vp), _int, _vp]),
     "csrk_spmv_dev_mc": (_int, [_vp, _vp, _int, _vp, _vp, _vp]),

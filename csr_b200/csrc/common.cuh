@@ -123,13 +123,16 @@ void dev_free(void *p, cudaStream_t s);
 
 // ------------------------------------------------------------------ matrix
 struct SpmvPlan;  // spmv.cu: tile map of the CSR kernel
-struct PsfPlan;   // spmv_psf.cu: panel/slab re-layout for large matrices
-struct Psf3Plan;  // spmv_psf3.cu: cell-tile slab kernel with TMA-staged entries
+struct StreamPlan;  // spmv_stream.cu: slab-major re-layout of the entries for the slab-stream kernel
+struct YOut;        // spmv.cuh
 
 // tunables settable through csrk_set_option (tests force the slab path on small inputs)
 struct Options {
-    std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab kernel v1, 3 cell-tile slab kernel
-    std::atomic<int64_t> psf_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a slab plan
+    std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab-stream kernel
+    std::atomic<int64_t> stream_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a stream plan
+    std::atomic<int64_t> stream_slab_bytes{0};          // > 0: cap on the x slab size (tests force many slabs)
+    std::atomic<int64_t> stream_ctas{0};                // > 0: CTAs (row groups) of the stream kernel instead of one per SM
+    std::atomic<int64_t> stream_warps{31};              // consumer warps per CTA of the stream kernel (1..31)
     std::atomic<int64_t> radix_bits{0};                 // digit width of the stable sort: 0 = pick (9 when it saves a pass), 8, 9
     std::atomic<int64_t> spmv_zero_copy_y{1};           // csrk_spmv: store rows straight into pinned host y
     std::atomic<int64_t> fix_threads{1024};             // threads per CTA of the fixed-point SpGEMM kernel (512 | 768 | 1024)
@@ -153,10 +156,8 @@ struct csrk_matrix {
     int64_t stat_products = -1, stat_out_nnz = -1;
     int stat_path = 0;  // dense numeric path of the product that made this matrix: 0 none, 1 owner-computes, 2 fixed point
     csrk::SpmvPlan *plan = nullptr;  // lazily built SpMV tile map
-    csrk::PsfPlan *psf[2] = {nullptr, nullptr};  // lazily built slab plans for float32 / float64 x
-    bool psf_failed[2] = {false, false};
-    csrk::Psf3Plan *psf3[2] = {nullptr, nullptr};
-    bool psf3_failed[2] = {false, false};
+    csrk::StreamPlan *stream[2] = {nullptr, nullptr};  // lazily built stream plans for float32 / float64 x
+    bool stream_failed[2] = {false, false};
     std::mutex mu;
 };
 
@@ -170,14 +171,10 @@ void plan_invalidate(csrk_matrix *m, cudaStream_t s);
 int normalize_rows_run(csrk_matrix *h, int kind, void *d_vec, cudaStream_t s);
 int from_coo_run(int32_t nrows, int32_t ncols, int64_t nnz, const int32_t *d_rows, const int32_t *d_cols,
                  const void *d_vals, int val_kind, csrk_matrix **out, cudaStream_t s);  // syncs internally
-void psf_destroy(PsfPlan *p, cudaStream_t s);
-int psf_build(csrk_matrix *h, int x_kind, PsfPlan **out, cudaStream_t s);  // syncs internally
-int psf_run(csrk_matrix *h, PsfPlan *p, const void *d_x, double *d_y, cudaStream_t s);
-int psf_panels(const PsfPlan *p);
-void psf3_destroy(Psf3Plan *p, cudaStream_t s);
-bool psf3_supported(const csrk_matrix *h, int x_kind);
-int psf3_build(csrk_matrix *h, int x_kind, Psf3Plan **out, cudaStream_t s);  // syncs internally
-int psf3_run(csrk_matrix *h, Psf3Plan *p, const void *d_x, double *d_y, cudaStream_t s);
+void stream_destroy(StreamPlan *p, cudaStream_t s);
+int stream_build(csrk_matrix *h, int x_kind, StreamPlan **out, cudaStream_t s);  // syncs internally; CSRK_EOVERFLOW = not representable
+int stream_run(csrk_matrix *h, StreamPlan *p, const void *d_x, const YOut &y, cudaStream_t s);
+void stream_info(const StreamPlan *p, int64_t *out /*[8]: G, NW, nslab, S, P, Q, n_split, smem*/);
 
 // ops implemented across the .cu files (all enqueue on `s`, no sync unless stated)
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s);

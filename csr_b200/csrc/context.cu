@@ -284,10 +284,8 @@ void matrix_destroy(csrk_matrix *m, cudaStream_t s)
     dev_free(m->ci, s);
     dev_free(m->vs, s);
     plan_destroy(m->plan, s);
-    psf_destroy(m->psf[0], s);
-    psf_destroy(m->psf[1], s);
-    psf3_destroy(m->psf3[0], s);
-    psf3_destroy(m->psf3[1], s);
+    stream_destroy(m->stream[0], s);
+    stream_destroy(m->stream[1], s);
     delete m;
 }
 
@@ -297,12 +295,9 @@ void plan_invalidate(csrk_matrix *m, cudaStream_t s)
     plan_destroy(m->plan, s);
     m->plan = nullptr;
     for (int k = 0; k < 2; k++) {
-        psf_destroy(m->psf[k], s);
-        m->psf[k] = nullptr;
-        m->psf_failed[k] = false;
-        psf3_destroy(m->psf3[k], s);
-        m->psf3[k] = nullptr;
-        m->psf3_failed[k] = false;
+        stream_destroy(m->stream[k], s);
+        m->stream[k] = nullptr;
+        m->stream_failed[k] = false;
     }
 }
 
@@ -373,10 +368,19 @@ int csrk_set_option(const char *name, int64_t value)
 {
     CSRK_ARG(name != nullptr, "option name is NULL");
     if (!strcmp(name, "spmv_mode")) {
-        CSRK_ARG(value >= 0 && value <= 3, "spmv_mode must be 0 (auto), 1 (tile), 2 (slab v1) or 3 (cell-tile slab)");
+        CSRK_ARG(value >= 0 && value <= 2, "spmv_mode must be 0 (auto), 1 (CSR tile kernel) or 2 (slab-stream kernel)");
         options().spmv_mode = value;
-    } else if (!strcmp(name, "psf_min_nnz")) {
-        options().psf_min_nnz = value;
+    } else if (!strcmp(name, "stream_min_nnz")) {
+        options().stream_min_nnz = value;
+    } else if (!strcmp(name, "stream_slab_bytes")) {
+        CSRK_ARG(value >= 0, "stream_slab_bytes must be >= 0");
+        options().stream_slab_bytes = value;
+    } else if (!strcmp(name, "stream_ctas")) {
+        CSRK_ARG(value >= 0, "stream_ctas must be >= 0");
+        options().stream_ctas = value;
+    } else if (!strcmp(name, "stream_warps")) {
+        CSRK_ARG(value >= 1 && value <= 31, "stream_warps must be 1..31");
+        options().stream_warps = value;
     } else if (!strcmp(name, "radix_bits")) {
         CSRK_ARG(value == 0 || value == 8 || value == 9, "radix_bits must be 0, 8 or 9");
         options().radix_bits = value;
@@ -414,6 +418,10 @@ int csrk_synchronize(void)
     return CSRK_OK;
 }
 
+// `s` is the stream the copies run on.  The handle's memory always comes from the LIBRARY stream's pool
+// allocation point (every later operation on the handle, and its cudaFreeAsync, run there), so for a
+// caller-owned stream (csrk_create_dev) the two streams are ordered explicitly: s waits for the allocation,
+// the library stream waits for the copies.
 static int create_impl(int32_t nrows, int32_t ncols, int64_t nnz, const void *rowptrs, int rp_is64,
                        const int32_t *colinds, const void *values, int val_kind, cudaStream_t s, cudaMemcpyKind kind,
                        csrk_h *out)
@@ -424,17 +432,36 @@ static int create_impl(int32_t nrows, int32_t ncols, int64_t nnz, const void *ro
     CSRK_ARG(rowptrs != nullptr, "rowptrs is NULL");
     CSRK_ARG(nnz == 0 || colinds != nullptr, "colinds is NULL");
     CSRK_ARG(val_kind == 0 || nnz == 0 || values != nullptr, "values is NULL but val_kind=%d", val_kind);
+    cudaStream_t ls = ctx().stream;
     csrk_matrix *m = nullptr;
-    CSRK_TRY(matrix_alloc(&m, nrows, ncols, nnz, rp_is64, val_kind, s));
-    cudaError_t e = cudaMemcpyAsync(m->rp, rowptrs, ((size_t)nrows + 1) * (rp_is64 ? 8 : 4), kind, s);
+    CSRK_TRY(matrix_alloc(&m, nrows, ncols, nnz, rp_is64, val_kind, ls));
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (s != ls) {
+        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(ev, ls);
+        if (e == cudaSuccess)
+            e = cudaStreamWaitEvent(s, ev, 0);
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(m->rp, rowptrs, ((size_t)nrows + 1) * (rp_is64 ? 8 : 4), kind, s);
     if (e == cudaSuccess && nnz)
         e = cudaMemcpyAsync(m->ci, colinds, (size_t)nnz * 4, kind, s);
     if (e == cudaSuccess && nnz && val_kind)
         e = cudaMemcpyAsync(m->vs, values, (size_t)nnz * val_kind, kind, s);
+    if (e == cudaSuccess && s != ls) {
+        e = cudaEventRecord(ev, s);
+        if (e == cudaSuccess)
+            e = cudaStreamWaitEvent(ls, ev, 0);
+    }
+    if (ev)
+        (void)cudaEventDestroy(ev);
     if (e == cudaSuccess && kind == cudaMemcpyHostToDevice)
         e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
-        matrix_destroy(m, s);
+        (void)cudaStreamSynchronize(s);
+        matrix_destroy(m, ls);
         return cuda_fail(e, "upload", __FILE__, __LINE__);
     }
     *out = m;
@@ -567,6 +594,20 @@ int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stre
     CSRK_TRY(ensure_init());
     cudaStream_t s = (cudaStream_t)stream;
     return spmv_run(h, d_x, x_kind, d_y, s);
+}
+
+int csrk_spmv_plan_info(csrk_h h, int x_kind, int64_t info[9])
+{
+    CSRK_ARG(h != nullptr && info != nullptr, "NULL argument");
+    CSRK_ARG(x_kind == 4 || x_kind == 8, "x_kind must be 4 or 8 (got %d)", x_kind);
+    for (int i = 0; i < 9; i++)
+        info[i] = 0;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (StreamPlan *p = h->stream[x_kind == 4 ? 0 : 1]) {
+        info[0] = 1;
+        stream_info(p, info + 1);
+    }
+    return CSRK_OK;
 }
 
 int csrk_spmv_dev_multi(csrk_h h, const void *d_x, int x_kind, double *const *d_ys, int n_out, void *stream)

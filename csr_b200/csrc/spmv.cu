@@ -24,6 +24,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "spmv.cuh"
 
 namespace csrk {
 
@@ -45,41 +46,6 @@ void plan_destroy(SpmvPlan *p, cudaStream_t s)
     dev_free(p->tile_row, s);
     delete p;
 }
-
-struct NoVal {};
-
-// Where a finished row goes: p[0] is this GPU's y; p[1..n) are the same segment inside the gather
-// buffers of the peer GPUs (NVLink peer memory), written by the same kernel so that the y
-// all-gather of the row-partitioned SpMV needs no separate collective.
-constexpr int SPMV_MAX_OUT = 8;
-struct YOut {
-    double *p[SPMV_MAX_OUT];
-    int n;
-    int mc;  // p[1] is an NVLink multicast (NVLS) address: ONE store lands in every GPU of the group
-};
-// `final` = the value is the row's result (not the head piece of a row that continues in later
-// tiles and gets its carries added by k_spmv_fixup): only final values leave the GPU.
-template <bool MULTI> __device__ __forceinline__ void store_y(const YOut &y, int64_t r, double v, bool final)
-{
-    y.p[0][r] = v;
-    if (!MULTI || !final)
-        return;
-    if (y.mc) {
-        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(y.p[1] + r), "d"(v) : "memory");
-        return;
-    }
-#pragma unroll
-    for (int k = 1; k < SPMV_MAX_OUT; k++)
-        if (k < y.n)
-            y.p[k][r] = v;
-}
-
-template <typename VT, typename XT> struct Prod {
-    using type = double;
-};
-template <> struct Prod<float, float> {
-    using type = float;
-};
 
 template <typename RPT>
 __global__ void k_spmv_plan(const RPT *__restrict__ rp, int32_t nrows, int64_t ntiles, int32_t *__restrict__ tile_row)
@@ -315,55 +281,40 @@ static int launch_spmv_v(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kin
     }
 }
 
-// The panel/slab kernel (spmv_psf.cu) is opt-in ("spmv_mode" = 2): measured on B200 at
-// 1M x 1M / 100M nnz it is still slower than the CSR tile kernel (0.50 ms vs 0.36 ms,
-// profiles/r01_spmv_psf_ncu.md: issue-bound segmented reduction on half-empty blocks plus
-// one exposed HBM latency per slab step), so auto mode stays on the tile kernel.
-static bool psf_wanted(const csrk_matrix *h, int x_kind, const void *d_x)
+// The slab-stream kernel (spmv_stream.cu) stages x in shared memory and reads a re-laid-out copy of the
+// entries; it pays G copies of x over the L2->SM fabric for never gathering x through L1/L2.  Auto mode
+// takes it when that trade wins: a matrix large enough to be worth a plan (one stable sort of the entries,
+// built on the first mult_vec of the handle) whose x, re-read once per SM, is smaller than its entry stream.
+static bool stream_wanted(const csrk_matrix *h, int x_kind, const void *d_x)
 {
-    if (options().spmv_mode.load() != 2 || ((uintptr_t)d_x & 15) != 0)  // TMA bulk copies need 16-byte aligned x
+    const int64_t mode = options().spmv_mode.load();
+    if (mode == 1 || ((uintptr_t)d_x & 15) != 0)  // TMA bulk copies need a 16-byte aligned x
         return false;
-    const int64_t nslabs = div_up((int64_t)h->ncols * x_kind, 64 * 1024);
-    return nslabs <= 4096 && h->nnz < ((int64_t)1 << 33);
+    if (mode == 2)
+        return true;
+    if (h->nnz < options().stream_min_nnz.load())
+        return false;
+    const double reload = (double)ctx().sm_count * (double)h->ncols * x_kind;
+    return reload <= (double)h->nnz * (4 + h->val_kind);
 }
 
-static int ensure_psf3(csrk_matrix *h, int x_kind, Psf3Plan **out)
+static int ensure_stream(csrk_matrix *h, int x_kind, StreamPlan **out)
 {
     const int k = x_kind == 4 ? 0 : 1;
     *out = nullptr;
     std::lock_guard<std::mutex> g(h->mu);
-    if (!h->psf3[k] && !h->psf3_failed[k]) {
-        Psf3Plan *p = nullptr;
-        const int rc = psf3_build(h, x_kind, &p, ctx().stream);
+    if (!h->stream[k] && !h->stream_failed[k]) {
+        StreamPlan *p = nullptr;
+        const int rc = stream_build(h, x_kind, &p, ctx().stream);
         if (rc == CSRK_EOVERFLOW) {
-            h->psf3_failed[k] = true;
+            h->stream_failed[k] = true;  // not representable (too many rows per SM): stay on the CSR kernel
             return CSRK_OK;
         }
         if (rc != CSRK_OK)
             return rc;
-        h->psf3[k] = p;
+        h->stream[k] = p;
     }
-    *out = h->psf3[k];
-    return CSRK_OK;
-}
-
-static int ensure_psf(csrk_matrix *h, int x_kind, PsfPlan **out)
-{
-    const int k = x_kind == 4 ? 0 : 1;
-    *out = nullptr;
-    std::lock_guard<std::mutex> g(h->mu);
-    if (!h->psf[k] && !h->psf_failed[k]) {
-        PsfPlan *p = nullptr;
-        const int rc = psf_build(h, x_kind, &p, ctx().stream);
-        if (rc == CSRK_EOVERFLOW) {
-            h->psf_failed[k] = true;  // not representable: stay on the CSR kernel
-            return CSRK_OK;
-        }
-        if (rc != CSRK_OK)
-            return rc;
-        h->psf[k] = p;
-    }
-    *out = h->psf[k];
+    *out = h->stream[k];
     return CSRK_OK;
 }
 
@@ -383,20 +334,11 @@ int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d
             CSRK_LAUNCH(k_zero_f64, (unsigned)div_up(h->nrows, 256), 256, 0, s, d_ys[k], (int64_t)h->nrows);
         return CSRK_OK;
     }
-    if (n_out == 1) {
-        const int64_t mode = options().spmv_mode.load();
-        if (mode == 2 && psf_wanted(h, x_kind, d_x)) {
-            PsfPlan *pp = nullptr;
-            CSRK_TRY(ensure_psf(h, x_kind, &pp));
-            if (pp)
-                return psf_run(h, pp, d_x, d_ys[0], s);
-        } else if (mode == 3 && ((uintptr_t)d_x & 15) == 0 && psf3_supported(h, x_kind) &&
-                   div_up((int64_t)h->ncols * x_kind, 32 * 1024) <= 60000 && h->nnz < ((int64_t)1 << 33)) {
-            Psf3Plan *pp = nullptr;
-            CSRK_TRY(ensure_psf3(h, x_kind, &pp));
-            if (pp)
-                return psf3_run(h, pp, d_x, d_ys[0], s);
-        }
+    if (stream_wanted(h, x_kind, d_x)) {
+        StreamPlan *sp = nullptr;
+        CSRK_TRY(ensure_stream(h, x_kind, &sp));
+        if (sp)
+            return stream_run(h, sp, d_x, yo, s);
     }
     SpmvPlan *p = nullptr;
     CSRK_TRY(ensure_plan(h, ctx().stream, &p));

@@ -63,7 +63,8 @@ def spgemm_row_weights(a, b_row_lengths, out_cols: int):
     bl = np.asarray(b_row_lengths, dtype=np.int64)
     if a.nnz == 0:
         return np.zeros(a.nrows, np.int64), np.zeros(a.nrows, np.int64)
-    prod = np.add.reduceat(bl[a.colinds], np.minimum(rp[:-1], a.nnz - 1)) * (lens > 0)
+    cum = np.concatenate([[0], np.cumsum(bl[a.colinds[:a.nnz]])])   # products of row i = cum[rp[i+1]] - cum[rp[i]]
+    prod = cum[rp[1:]] - cum[rp[:-1]]
     z_est = out_cols * -np.expm1(-prod / max(out_cols, 1))
     return (prod + 0.45 * z_est).astype(np.int64), prod
 
@@ -224,6 +225,10 @@ class DistSpMV:
     def set_x(self, x_host):
         "Load x on the root (other ranks receive it in step())."
         self.x.copy_(self.torch.as_tensor(np.ascontiguousarray(x_host)).to(self.x.dtype), non_blocking=False)
+        if self.x_in is not self.x:
+            # under NVLS the kernels read the symmetric buffer, which step() fills by multicast: keep the
+            # local copy in step with x so that local_spmv() is valid right after set_x()
+            self.x_in[:self.ncols].copy_(self.x)
 
     def local_spmv(self):
         "Only the local kernel(s), no collectives (bench.py times this for the roofline)."
@@ -265,6 +270,9 @@ class DistSpMV:
         if self.symm is not None:
             # one kernel computes the rows and scatters them to every rank over NVLink
             stream = self.torch.cuda.current_stream().cuda_stream
+            # entry barrier: no rank may store rows into a peer's buffer while that peer still reads the
+            # previous result (the broadcast above orders every rank after the ROOT only)
+            self.symm.barrier()
             self.kernel.mult_vec_dev_multi(self.handle, self.x.data_ptr(), self.x.element_size(), self.peer_ptrs, stream)
             self.symm.barrier()   # all ranks' segments have landed everywhere
             return self.ybuf

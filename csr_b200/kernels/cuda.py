@@ -310,9 +310,21 @@ def from_device_arrays(nrows, ncols, nnz, rowptrs_ptr, rp_is64, colinds_ptr, val
     return cuda_h(out.value, nrows, ncols, nnz, csr_cls)
 
 
+def spmv_plan_info(h: cuda_h, x_itemsize: int = 4) -> dict:
+    """Which SpMV kernel serves ``h`` for x of the given item size (the plan is built by the first
+    ``mult_vec`` that selects it): ``{'kernel': 'stream' | 'tile', ...plan shape}``."""
+    info = (C.c_int64 * 9)()
+    N.check(N.lib().csrk_spmv_plan_info(_live(h), int(x_itemsize), info), "spmv_plan_info")
+    names = ("ctas", "warps", "slabs", "slab_cols", "rows_per_warp", "pseudo_rows", "split_rows", "smem_bytes")
+    out = {"kernel": "stream" if info[0] else "tile"}
+    if info[0]:
+        out.update({n: int(info[i + 1]) for i, n in enumerate(names)})
+    return out
+
+
 def set_option(name: str, value: int) -> None:
-    """Library tunables: ``spmv_mode`` (0 auto, 1 CSR tile kernel, 2 panel/slab kernel),
-    ``psf_min_nnz`` (smallest nnz for which auto mode builds a slab plan)."""
+    """Library tunables (``include/csrk.h``): ``spmv_mode`` (0 auto, 1 CSR tile kernel, 2 slab-stream
+    kernel), ``stream_min_nnz``, ``stream_slab_bytes``, ``stream_ctas``, ``stream_warps``, ..."""
     N.check(N.lib().csrk_set_option(name.encode(), int(value)), "set_option")
 
 

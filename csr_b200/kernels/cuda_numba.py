@@ -82,6 +82,11 @@ def mult_vec(h, x):
     xv = _kernel_vector(x)
     y = np.empty(nrows, np.float64)
     rc = _spmv(h, xv.ctypes.data, xv.itemsize, y.ctypes.data)
+    # xv may be a temporary (dtype promotion / contiguous copy).  Numba releases a variable after its LAST
+    # use, and taking ``xv.ctypes.data`` is a use that ends before the call: without this read the buffer
+    # could be freed (and reused by another nogil thread) while the native code still reads it.
+    if xv.shape[0] != ncols:
+        rc = 1
     if rc == 1:
         raise ValueError("mult_vec: bad argument")
     if rc != 0:

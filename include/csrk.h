@@ -61,8 +61,10 @@ int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t csrk_launch_count(void);
 int csrk_synchronize(void);
-/* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 panel/slab kernel;
- * "psf_min_nnz" smallest nnz for which auto mode builds a slab plan;
+/* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 slab-stream kernel (x staged in shared memory);
+ * "stream_min_nnz" smallest nnz for which auto mode builds a stream plan;
+ * "stream_slab_bytes" > 0 caps the x slab size, "stream_ctas" > 0 sets the number of CTAs (row groups),
+ *               "stream_warps" 1..31 the consumer warps per CTA of the slab-stream kernel (tests, tuning);
  * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
  * "spmv_zero_copy_y" 1 | 0: csrk_spmv stores finished rows straight into y when y is pinned host memory;
  * "fix_threads" 512 | 768 | 1024 threads per CTA of that kernel (default 1024);
@@ -85,7 +87,9 @@ int csrk_create(int32_t nrows, int32_t ncols, int64_t nnz,
                 const int32_t *colinds,
                 const void *values, int val_kind,
                 csrk_h *out);
-/* Same, from device pointers (D2D copy on `stream`). */
+/* Same, from device pointers.  The D2D copies are enqueued on `stream` (the source arrays may be reused
+ * once work enqueued on `stream` after this call has run) and the library stream is made to wait for
+ * them, so the handle may be used by any entry point right away; the call does not synchronise. */
 int csrk_create_dev(int32_t nrows, int32_t ncols, int64_t nnz,
                     const void *d_rowptrs, int rp_is64,
                     const int32_t *d_colinds,
@@ -108,6 +112,11 @@ int csrk_subset_rows(csrk_h h, int32_t begin, int32_t end, csrk_h *out);
  * (cudaHostAlloc / cudaHostRegister, e.g. a torch pin_memory() tensor) the kernel writes each finished
  * row directly into it over PCIe, overlapping the device-to-host transfer with the compute. */
 int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y);
+/* Which SpMV kernel serves this handle for x of x_kind, and the shape of its plan:
+ * info[0] = 1 when a slab-stream plan exists (built by the first mult_vec that selected it), else 0 (CSR
+ * tile kernel); info[1..8] = CTAs, consumer warps per CTA, x slabs, columns per slab, pseudo-rows per warp,
+ * pseudo-rows, split rows, shared-memory bytes per CTA. */
+int csrk_spmv_plan_info(csrk_h h, int x_kind, int64_t info[9]);
 /* Device pointers; y has nrows doubles. */
 int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stream);
 /* Fused SpMV + gather for the row-partitioned multi-GPU SpMV: every finished row is stored to

@@ -16,7 +16,7 @@ import pytest
 
 from oracle import oracle as orc
 from util import (cases, gmat, canonical, assert_same_structure, assert_values_close, value_tol,
-                  abs_product_scale)
+                  spgemm_terms, spmv_terms)
 
 pytestmark = pytest.mark.gpu
 
@@ -35,9 +35,7 @@ def test_mult_vec(kernel, golden, name):
         kernel.release_handle(h)
     assert y.dtype == np.float64 and y.shape == (a.nrows,)
     f4 = (a.values is not None and a.values.dtype == np.float32) or x.dtype == np.float32
-    vmax = 1.0 if a.values is None else np.abs(a.values).max(initial=0.0)
-    scale = float(vmax) * float(np.abs(x).max(initial=0.0)) * max(int(np.diff(a.rowptrs).max(initial=0)), 1) ** 0.5
-    assert_values_close(y, ref, 1e-5 if f4 else 1e-10, scale)
+    assert_values_close(y, ref, 1e-5 if f4 else 1e-10, spmv_terms(a, x))
 
 
 @pytest.mark.parametrize("name", cases(_Z, "mult_ab") + cases(_Z, "mult_abt"))
@@ -59,21 +57,22 @@ def test_multiply(kernel, golden, name):
     rp, ci, vs = canonical(c)
     assert_same_structure(got, rp, ci)
     assert got.values.dtype == np.float64
-    assert_values_close(got.values, vs, value_tol(a, b), abs_product_scale(a, b))
+    assert_values_close(got.values, vs, value_tol(a, b), spgemm_terms(a, b, tr))
     assert stats["out_nnz"] == c.nnz
 
 
 @pytest.mark.parametrize("name", cases(_Z, "mult_ab") + cases(_Z, "mult_abt"))
 def test_csr_multiply_filters_zeros(kernel, golden, name):
     "CSR.multiply == reference CSR.multiply (stored zeros dropped, csr.py:555)."
-    a, b, cf = (gmat(golden, f"{name}.{k}") for k in ("a", "b", "cf"))
+    a, b, c, cf = (gmat(golden, f"{name}.{k}") for k in ("a", "b", "c", "cf"))
     got = a.multiply(b, transpose=name.startswith("abt_"))
     if got.nnz != cf.nnz:
         # exact cancellation can differ with summation order only when |value| ~ rounding noise
         pytest.skip("cancellation pattern differs from the reference's summation order")
     rp, ci, vs = canonical(cf)
     assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
-    assert_values_close(got.values, vs, value_tol(a, b), abs_product_scale(a, b))
+    keep = canonical(c)[2] != 0   # the bound for the kept entries (cf = c without its stored zeros)
+    assert_values_close(got.values, vs, value_tol(a, b), spgemm_terms(a, b, name.startswith("abt_"))[keep])
     assert np.all(got.values != 0)
 
 

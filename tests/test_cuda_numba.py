@@ -11,6 +11,7 @@ from numba import njit  # noqa: E402
 
 from csr_b200 import synth  # noqa: E402
 from csr_b200.kernels import cuda_numba as cn  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -35,12 +36,21 @@ def test_mult_vec_from_nopython(kernel, dtype):
     A = synth.powerlaw_csr(5000, 3000, 200000, seed=31, dtype=dtype, alpha=1.0)
     h = kernel.to_handle(A)
     try:
+        # contiguous floats alias the caller's array; integers and strided views make the nopython
+        # wrapper build a TEMPORARY that must stay alive across the native call
+        strided = synth.dense_vector(2 * A.ncols, 3, "f8")[::2]
+        strided4 = synth.dense_vector(3 * A.ncols, 4, "f4")[1::3]
         for x in (synth.dense_vector(A.ncols, 1, "f8"), synth.dense_vector(A.ncols, 2, "f4"),
-                  np.arange(A.ncols, dtype=np.int64) % 7):
+                  np.arange(A.ncols, dtype=np.int64) % 7, strided, strided4,
+                  (np.arange(A.ncols) % 3 == 0)):
             y, nrm = _power_step(h.H, x)
             ref = kernel.mult_vec(h, x)
             assert y.dtype == np.float64 and np.array_equal(y, ref)
             assert nrm == pytest.approx(np.sqrt((ref * ref).sum()))
+            xo = np.ascontiguousarray(x if x.dtype in (np.float32, np.float64) else x.astype(np.float64))
+            want = orc.mult_vec(A, xo)
+            f4 = dtype == "f4" or xo.dtype == np.float32
+            assert np.allclose(y, want, rtol=1e-5 if f4 else 1e-10, atol=(1e-5 if f4 else 1e-10) * np.abs(want).max())
         assert tuple(int(v) for v in cn.dims(h.H)) == (A.nrows, A.ncols, A.nnz, 0, A.values.dtype.itemsize)
         with pytest.raises(ValueError):
             _power_step(h.H, np.zeros(A.ncols + 1))
@@ -61,3 +71,6 @@ def test_product_and_export_from_nopython(kernel):
     assert (nr, nc, nnz) == (ref.nrows, ref.ncols, ref.nnz)
     assert rp.dtype == np.int64 and np.array_equal(rp, ref.rowptrs) and np.array_equal(ci, ref.colinds)
     assert np.allclose(vs, ref.values, rtol=1e-12, atol=0.0)
+    want = orc.canonical(orc.mult_abt(A, A))          # and against the oracle, not only CUDA against CUDA
+    assert np.array_equal(rp, want.rowptrs) and np.array_equal(ci, want.colinds)
+    assert np.allclose(vs, want.values, rtol=1e-10, atol=0.0)

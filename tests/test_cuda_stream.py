@@ -1,7 +1,8 @@
 """
-GPU: the panel/slab SpMV kernels (csr_b200/csrc/spmv_psf.cu, spmv_psf3.cu), forced on through the
-``spmv_mode`` option so that small inputs exercise it, against the golden vectors,
-the oracle and the CSR tile kernel.
+GPU: the slab-stream SpMV kernel (csr_b200/csrc/spmv_stream.cu: x staged in shared memory, entries re-laid
+out per warp and slab), forced on through the ``spmv_mode`` option so that small inputs exercise it --
+with small x slabs, few CTAs and few warps so that cells, pieces, carries and the block-to-block run
+hand-over all occur -- against the golden vectors, the oracle and the CSR tile kernel.
 """
 
 import os
@@ -18,16 +19,25 @@ pytestmark = pytest.mark.gpu
 _Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
 
 
-@pytest.fixture(params=[2, 3], ids=["v1", "celltile"])
+# (slab bytes, CTAs, consumer warps): library defaults; tiny slabs + one warp per CTA (long streams, many
+# cells per warp); 2 KB slabs on 7 CTAs x 3 warps
+CONFIGS = {"default": (0, 0, 31), "tiny-slabs": (512, 4, 1), "mid": (2048, 7, 3)}
+
+
+@pytest.fixture(params=list(CONFIGS), ids=list(CONFIGS))
 def slab(kernel, request):
-    """Both slab designs: 2 = spmv_psf.cu, 3 = spmv_psf3.cu (cell-tile, TMA-staged entries; dtype
-    combinations it does not cover fall back to the CSR tile kernel)."""
-    kernel.set_option("spmv_mode", request.param)
-    kernel._slab_mode = request.param
+    sb, ctas, warps = CONFIGS[request.param]
+    kernel.set_option("spmv_mode", 2)
+    kernel.set_option("stream_slab_bytes", sb)
+    kernel.set_option("stream_ctas", ctas)
+    kernel.set_option("stream_warps", warps)
     try:
         yield kernel
     finally:
         kernel.set_option("spmv_mode", 0)
+        kernel.set_option("stream_slab_bytes", 0)
+        kernel.set_option("stream_ctas", 0)
+        kernel.set_option("stream_warps", 31)
 
 
 def _scale(A, x):
@@ -40,8 +50,12 @@ def _run(kernel, A, x):
     try:
         y1 = kernel.mult_vec(h, x)
         y2 = kernel.mult_vec(h, x)      # second call reuses the cached plan
+        xk = 4 if np.asarray(x).dtype == np.float32 else 8
+        info = kernel.spmv_plan_info(h, xk)
     finally:
         kernel.release_handle(h)
+    if A.nnz and A.nrows:
+        assert info["kernel"] == "stream", info     # the kernel under test really ran
     assert np.array_equal(y1, y2, equal_nan=True), "slab SpMV must be deterministic"
     return y1
 
@@ -98,8 +112,11 @@ def test_matches_tile_kernel_and_nonfinite(slab):
     x[11] = np.nan
     y = _run(slab, A, x)
     slab.set_option("spmv_mode", 1)
-    yt = _run(slab, A, x)
-    slab.set_option("spmv_mode", slab._slab_mode)
+    h = slab.to_handle(A)
+    yt = slab.mult_vec(h, x)
+    assert slab.spmv_plan_info(h, 8)["kernel"] == "tile"
+    slab.release_handle(h)
+    slab.set_option("spmv_mode", 2)
     bad = ~np.isfinite(yt)
     assert np.array_equal(~np.isfinite(y), bad), "inf/nan must propagate to exactly the same rows"
     assert np.array_equal(np.isnan(y), np.isnan(yt))
@@ -122,3 +139,48 @@ def test_plan_survives_order_columns_and_filter(slab):
         slab.release_handle(h)
     for y in (y0, y1, y2):
         assert_values_close(y, ref, 1e-10, _scale(A, x))
+
+
+def test_split_rows_and_block_handover(slab):
+    "Rows far longer than a piece (4096) and than a 128-entry block; structure-only and int64 rowptrs too."
+    for values, rp64 in ((True, False), (False, True)):
+        A = synth.powerlaw_csr(300, 30000, 600000, seed=61, dtype="f8", alpha=1.2, values=values)
+        assert int(np.diff(A.rowptrs).max()) > 3 * 4096
+        if rp64:
+            A = CSR(A.nrows, A.ncols, A.nnz, A.rowptrs.astype(np.int64), A.colinds, A.values, _cast=False)
+        x = synth.dense_vector(A.ncols, 62, "f8")
+        y = _run(slab, A, x)
+        assert_values_close(y, orc.mult_vec(A, x), 1e-10, _scale(A, x))
+
+
+def test_empty_rows_and_columns(slab):
+    "Empty rows give exactly 0.0; x entries that no column touches may be non-finite."
+    A = synth.powerlaw_csr(5000, 9000, 40000, seed=71, dtype="f4", alpha=1.0)
+    rows = np.repeat(np.arange(A.nrows), np.diff(A.rowptrs))
+    keep = (A.colinds % 5 != 0) & (rows % 3 != 0)
+    B = CSR.from_coo(rows[keep], A.colinds[keep], A.values[keep], (A.nrows, A.ncols))
+    x = synth.dense_vector(B.ncols, 72, "f4")
+    x[::5] = np.nan                      # never referenced
+    y = _run(slab, B, x)
+    ref = orc.mult_vec(B, x)
+    assert np.isfinite(y).all()
+    assert np.all(y[np.diff(B.rowptrs) == 0] == 0.0)
+    assert_values_close(y, ref, 1e-5, _scale(B, np.where(np.isfinite(x), x, 0.0)))
+
+
+def test_auto_mode_picks_by_cost_model(kernel):
+    "auto: the stream kernel only when the matrix is large and x (re-read per SM) is smaller than the entry stream"
+    kernel.set_option("stream_min_nnz", 100000)
+    try:
+        A = synth.powerlaw_csr(20000, 1000, 400000, seed=81, dtype="f4", alpha=0.8)      # 148*4 KB << 3.2 MB
+        Bm = synth.powerlaw_csr(2000, 200000, 150000, seed=82, dtype="f4", alpha=0.8)    # 148*800 KB >> 1.2 MB
+        for M, want in ((A, "stream"), (Bm, "tile")):
+            x = synth.dense_vector(M.ncols, 83, "f4")
+            h = kernel.to_handle(M)
+            y = kernel.mult_vec(h, x)
+            info = kernel.spmv_plan_info(h, 4)
+            kernel.release_handle(h)
+            assert info["kernel"] == want, info
+            assert_values_close(y, orc.mult_vec(M, x), 1e-5, _scale(M, x))
+    finally:
+        kernel.set_option("stream_min_nnz", 4000000)

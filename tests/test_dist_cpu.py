@@ -128,3 +128,12 @@ def test_spgemm_row_weights_model():
     E = synth.powerlaw_csr(10, 20, 0, seed=1, dtype="f8")
     w0, p0 = spgemm_row_weights(E, np.diff(B.rowptrs)[:20], 5)
     assert w0.sum() == 0 and p0.sum() == 0
+
+
+def test_spgemm_row_weights_trailing_empty_rows():
+    "the last non-empty row keeps ALL its products when empty rows follow it (ADVICE r1)"
+    from csr_b200 import CSR
+    from csr_b200.dist import spgemm_row_weights
+    A = CSR(3, 3, 3, np.array([0, 3, 3, 3]), np.array([0, 1, 2]), np.ones(3))
+    _, prod = spgemm_row_weights(A, np.array([5, 7, 11]), 100)
+    assert list(prod) == [23, 0, 0]

@@ -146,7 +146,7 @@ def test_known_answer_from_reference_tests():
     "tests/test_transpose.py:11-27 builds this matrix"
     m = CSR.from_coo(np.array([0, 0, 1, 3]), np.array([1, 2, 0, 1]), np.array([0, 1, 2, 3], np.float64), (4, 3))
     assert list(m.rowptrs) == [0, 2, 3, 3, 4]
-    assert np.array_equal(m.row(0), [0, 0, 1])
+    assert list(m.row_cs(0)) == [1, 2] and list(m.row_vs(0)) == [0.0, 1.0]
     assert np.array_equal(m.to_scipy().toarray(), [[0, 0, 1], [2, 0, 0], [0, 0, 0], [0, 3, 0]])
 
 

@@ -38,23 +38,36 @@ def value_tol(*mats):
     return 1e-5 if f4 else 1e-10
 
 
-def assert_values_close(got, ref, rtol, scale=None):
-    """|got-ref| <= rtol * (|ref| + scale): `scale` is the magnitude of the terms that
-    were summed, so cancellation does not turn a reordering into a false failure."""
+def assert_values_close(got, ref, rtol, terms=None):
+    """|got - ref| <= rtol * max(|ref|, terms), element by element.  ``terms`` is the magnitude of what was
+    summed into each element -- ``spgemm_terms`` / ``spmv_terms`` below: sum_k |a_ik||b_kj| resp.
+    sum_i |a_i||x_i|, one oracle call on the absolute values -- the standard bound for a re-ordered sum, so
+    that cancellation does not turn a different summation order into a false failure.  Without ``terms``
+    the bound is purely relative."""
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
     assert got.shape == ref.shape
-    if scale is None:
-        scale = np.abs(ref).max(initial=0.0)
+    mag = np.abs(ref) if terms is None else np.maximum(np.abs(ref), np.asarray(terms, np.float64))
     err = np.abs(got - ref)
-    bound = rtol * (np.abs(ref) + scale) + 1e-300
-    bad = ~(err <= bound) & ~(np.isnan(got) & np.isnan(ref))
-    assert not bad.any(), f"max err {err.max()} at {int(np.argmax(err))} (rtol {rtol})"
+    bad = ~(err <= rtol * mag + 1e-300) & ~(np.isnan(got) & np.isnan(ref)) & ~((got == ref) & np.isinf(ref))
+    assert not bad.any(), f"max err {np.nanmax(np.where(bad, err, 0))} at {int(np.argmax(bad))} (rtol {rtol})"
 
 
-def abs_product_scale(a, b, transpose=False):
-    "Row-wise upper bound sum |a||b| for an SpGEMM result, as a dense-free scalar per matrix."
-    av = np.abs(a.values).max(initial=0.0) if a.values is not None else 1.0
-    bv = np.abs(b.values).max(initial=0.0) if b.values is not None else 1.0
-    la = np.diff(np.asarray(a.rowptrs).astype(np.int64)).max(initial=0)
-    return float(av) * float(bv) * max(int(la), 1)
+def _abs_mat(m):
+    from oracle import oracle as orc
+    vs = np.ones(m.nnz) if m.values is None else np.abs(np.asarray(m.values, dtype=np.float64))
+    return orc.Mat(m.nrows, m.ncols, m.nnz, np.asarray(m.rowptrs), np.asarray(m.colinds), vs)
+
+
+def spgemm_terms(a, b, transpose=False):
+    "sum_k |a_ik| |b_kj| for every stored element of A B (or A B^T), in canonical (row, column) order."
+    from oracle import oracle as orc
+    c = (orc.mult_abt if transpose else orc.mult_ab)(_abs_mat(a), _abs_mat(b))
+    return canonical(c)[2]
+
+
+def spmv_terms(a, x):
+    "sum_i |a_ri| |x_i| for every row (non-finite x entries count as 0: they are checked separately)."
+    from oracle import oracle as orc
+    xa = np.abs(np.asarray(x, dtype=np.float64))
+    return orc.mult_vec(_abs_mat(a), np.where(np.isfinite(xa), xa, 0.0))
