@@ -18,10 +18,14 @@
 //   * a warp's entries are stored as ONE contiguous stream ordered by slab ("cells"), 8 bytes per entry as
 //     in CSR: a packed word (local row << 16 | column inside the slab) and the value.  Inside a cell the
 //     entries keep CSR order, so the entries of a pseudo-row are adjacent.
-//   * a lane takes 4 consecutive entries (two 128-bit loads), sums runs of equal rows in registers
-//     (float64), and the warp joins the runs that cross lanes with ONE segmented shuffle scan per 128
-//     entries; every (pseudo-row, slab) run then costs one plain read-modify-write of the warp's private
-//     float64 accumulators in shared memory.  No atomics anywhere: results are deterministic.
+//   * a lane takes 8 consecutive entries (128-bit loads), sums runs of equal rows in registers (float64)
+//     and adds every finished run to the warp's private float64 accumulators in shared memory with a plain
+//     read-modify-write.  Runs that cross lanes: when no row fills a whole lane a row can only sit in the
+//     tail of one lane and the head of the next, so all tails are flushed first and all heads second
+//     (never the same address in one instruction); blocks with longer runs join them with one segmented
+//     shuffle scan.  No atomics anywhere: results are deterministic.
+//   * cells are padded to multiples of 8 entries with INERT entries (value 0, column S = a slot of the
+//     slab buffer that always holds 0.0, row = the row before them), so the kernel never tests entries.
 //   * pieces of split rows go to a carry array and a tiny fix-up kernel adds them in piece order.
 //
 // Cost model: HBM bytes are the stream (nnz*(4+V)) + x once + y; the L2->SM fabric carries
@@ -35,7 +39,7 @@
 
 namespace csrk {
 
-constexpr int ST_E = 4;                    // entries per lane per block (one 128-bit load of packed words)
+constexpr int ST_E = 8;                    // entries per lane per block (two 128-bit loads of packed words)
 constexpr int ST_BLK = 32 * ST_E;          // entries per warp block
 constexpr int ST_PIECE = 4096;             // longest pseudo-row
 constexpr uint32_t ST_NOROW = 0xffffffffu;
@@ -49,7 +53,8 @@ struct StreamPlan {
     int n_split = 0;
     uint32_t *idx = nullptr;   // [npad]  local row << 16 | column - slab*S
     void *val = nullptr;       // [npad]  VT (absent for structure-only matrices)
-    int64_t *ends = nullptr;   // [G*NW][nslab+1]: [b][0] = start of bin b's stream, [b][s+1] = end of cell s
+    int64_t *binbase = nullptr;  // [G*NW] start of bin b's stream
+    uint32_t *cstart = nullptr;  // [G*NW][nslab+1] start of cell s relative to the bin's stream ([nslab] = its end); multiples of 8
     int32_t *rowmap = nullptr; // [G*NW][P]: >= 0 row of y, -1 unused, <= -2 carry slot -(v+2)
     int32_t *split = nullptr;  // [3*n_split]: row, first carry slot, number of pieces
 };
@@ -60,7 +65,8 @@ void stream_destroy(StreamPlan *p, cudaStream_t s)
         return;
     dev_free(p->idx, s);
     dev_free(p->val, s);
-    dev_free(p->ends, s);
+    dev_free(p->binbase, s);
+    dev_free(p->cstart, s);
     dev_free(p->rowmap, s);
     dev_free(p->split, s);
     delete p;
@@ -168,23 +174,21 @@ __global__ void k_st_keys(const RPT *__restrict__ rp, const int32_t *__restrict_
 
 struct StPadLoader {
     const int64_t *cs;
-    __device__ __forceinline__ int64_t operator()(int64_t k) const { return (cs[k + 1] - cs[k] + 3) & ~(int64_t)3; }
+    __device__ __forceinline__ int64_t operator()(int64_t k) const { return (cs[k + 1] - cs[k] + ST_E - 1) & ~(int64_t)(ST_E - 1); }
 };
 
-__global__ void k_st_ends(const int64_t *__restrict__ cs, const int64_t *__restrict__ pstart, int B, int nslab,
-                          int64_t *__restrict__ ends)
+__global__ void k_st_cells(const int64_t *__restrict__ pstart, int B, int nslab, int64_t *__restrict__ binbase,
+                           uint32_t *__restrict__ cstart)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * (nslab + 1))
         return;
     const int64_t b = i / (nslab + 1);
     const int s = (int)(i % (nslab + 1));
-    if (s == 0) {
-        ends[i] = pstart[b * nslab];
-    } else {
-        const int64_t k = b * nslab + s - 1;
-        ends[i] = pstart[k] + (cs[k + 1] - cs[k]);
-    }
+    const int64_t base = pstart[b * nslab];
+    if (s == 0)
+        binbase[b] = base;
+    cstart[i] = (uint32_t)(pstart[b * nslab + s] - base);
 }
 
 template <typename VT>
@@ -200,6 +204,25 @@ __global__ void k_st_place(const int32_t *__restrict__ skeys, const int32_t *__r
     idx[dst] = (uint32_t)spacked[i];
     if constexpr (!std::is_same<VT, NoPayload>::value)
         val[dst] = svals[i];
+}
+
+// inert entries behind the last real entry of every cell: same row, column S (always 0.0), value 0
+template <typename VT>
+__global__ void k_st_pad(const int32_t *__restrict__ spacked, const int64_t *__restrict__ cs, const int64_t *__restrict__ pstart,
+                         int64_t ncells, int S, uint32_t *__restrict__ idx, VT *__restrict__ val)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncells)
+        return;
+    const int64_t cnt = cs[k + 1] - cs[k];
+    if (cnt == 0 || (cnt & (ST_E - 1)) == 0)
+        return;
+    const uint32_t word = ((uint32_t)spacked[cs[k + 1] - 1] & 0xffff0000u) | (uint32_t)S;
+    for (int64_t p = pstart[k] + cnt; p < pstart[k + 1]; p++) {
+        idx[p] = word;
+        if constexpr (!std::is_same<VT, NoPayload>::value)
+            val[p] = VT(0);
+    }
 }
 
 static int st_bits(int64_t n)
@@ -233,8 +256,9 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     const size_t smem_max = ctx().smem_optin;
     if (P->P > 65534 || acc_bytes + 64 + 2 * 8192 > smem_max)
         return CSRK_EOVERFLOW;  // too many rows for shared-memory accumulators: stay on the tile kernel
-    int64_t slab = (int64_t)((smem_max - acc_bytes - 64) / 2) & ~(int64_t)127;
-    slab = std::min<int64_t>(slab, (int64_t)65536 * P->x_kind);
+    // a buffer is one slab + 128 bytes (the always-zero slot the inert entries point at)
+    int64_t slab = (int64_t)((smem_max - acc_bytes - 64) / 2 - 128) & ~(int64_t)127;
+    slab = std::min<int64_t>(slab, (int64_t)65408 * P->x_kind);   // columns inside a slab (and the zero slot) fit 16 bits
     slab = std::min<int64_t>(slab, (((int64_t)h->ncols * P->x_kind) + 127) & ~(int64_t)127);
     const int64_t cap = options().stream_slab_bytes.load();
     if (cap > 0)
@@ -243,10 +267,10 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     P->slab_bytes = (int)slab;
     P->S = (int)(slab / P->x_kind);
     P->nslab = (int)std::max<int64_t>(div_up((int64_t)h->ncols, P->S), 1);
-    P->smem_bytes = 2 * (size_t)slab + acc_bytes + 64;
+    P->smem_bytes = 2 * ((size_t)slab + 128) + acc_bytes + 64;
     const int64_t ncells = (int64_t)B * P->nslab;
-    if (ncells >= ((int64_t)1 << 30))
-        return CSRK_EOVERFLOW;
+    if (ncells >= ((int64_t)1 << 30) || nnz / B + 2 * ST_PIECE + (int64_t)ST_E * P->nslab >= ((int64_t)1 << 31))
+        return CSRK_EOVERFLOW;   // cell offsets inside a bin's stream are 32-bit
 
     DevBuf qkey, qid, qdest, order, qbl, splitcnt;
     CSRK_TRY(qkey.alloc(sizeof(int32_t) * (size_t)Q, s));
@@ -287,22 +311,25 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
                                     spacked.as<int32_t>(), HASV ? svals.as<VT>() : nullptr, s, skeys.as<int32_t>())));
     CSRK_TRACE_MARK("stream plan: entries sorted", s);
 
-    // 4. cells padded to multiples of 4 entries (16-byte loads), bin streams contiguous
+    // 4. cells padded to multiples of 8 entries (a lane's share), bin streams contiguous
     DevBuf cs, pstart;
     CSRK_TRY(cs.alloc(sizeof(int64_t) * ((size_t)ncells + 1), s));
     CSRK_TRY(pstart.alloc(sizeof(int64_t) * ((size_t)ncells + 1), s));
     CSRK_LAUNCH((k_key_bounds<int64_t>), (unsigned)div_up(div_up(nnz + 1, 4), 256), 256, 0, s, skeys.as<int32_t>(), nnz,
                 (int32_t)ncells, cs.as<int64_t>());
     CSRK_TRY((exclusive_scan<int64_t>(StPadLoader{cs.as<int64_t>()}, ncells, pstart.as<int64_t>(), s)));
-    const size_t npad = (size_t)nnz + 3 * (size_t)ncells + 4;
+    const size_t npad = (size_t)nnz + (ST_E - 1) * (size_t)ncells + ST_E;
     CSRK_TRY(dev_alloc((void **)&P->idx, sizeof(uint32_t) * npad, s));
     if (HASV)
         CSRK_TRY(dev_alloc(&P->val, sizeof(VT) * npad, s));
-    CSRK_TRY(dev_alloc((void **)&P->ends, sizeof(int64_t) * (size_t)B * (P->nslab + 1), s));
-    CSRK_LAUNCH(k_st_ends, (unsigned)div_up((int64_t)B * (P->nslab + 1), 256), 256, 0, s, cs.as<int64_t>(),
-                pstart.as<int64_t>(), B, P->nslab, P->ends);
+    CSRK_TRY(dev_alloc((void **)&P->binbase, sizeof(int64_t) * (size_t)B, s));
+    CSRK_TRY(dev_alloc((void **)&P->cstart, sizeof(uint32_t) * (size_t)B * (P->nslab + 1), s));
+    CSRK_LAUNCH(k_st_cells, (unsigned)div_up((int64_t)B * (P->nslab + 1), 256), 256, 0, s, pstart.as<int64_t>(), B,
+                P->nslab, P->binbase, P->cstart);
     CSRK_LAUNCH((k_st_place<VT>), (unsigned)div_up(nnz, 256), 256, 0, s, skeys.as<int32_t>(), spacked.as<int32_t>(),
                 HASV ? svals.as<VT>() : nullptr, nnz, cs.as<int64_t>(), pstart.as<int64_t>(), P->idx, (VT *)P->val);
+    CSRK_LAUNCH((k_st_pad<VT>), (unsigned)div_up(ncells, 256), 256, 0, s, spacked.as<int32_t>(), cs.as<int64_t>(),
+                pstart.as<int64_t>(), ncells, P->S, P->idx, (VT *)P->val);
     CSRK_CUDA(cudaMemcpyAsync(&P->n_split, splitcnt.as<int>(), sizeof(int), cudaMemcpyDeviceToHost, s));
     CSRK_CUDA(cudaStreamSynchronize(s));
     CSRK_TRACE_MARK("stream plan: placed", s);
@@ -386,17 +413,20 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint32_t *p)
     return make_uint4((uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w);
 }
 
-// the 4 values of a lane (nothing for a structure-only matrix)
+// the 8 values of a lane (nothing for a structure-only matrix)
 template <typename VT> struct StVals {
     VT v[ST_E];
     __device__ __forceinline__ void load(const VT *p)
     {
         if constexpr (sizeof(VT) == 4) {
-            const float4 q = ld_stream_float4(p);
-            v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+            const float4 a = ld_stream_float4(p), b = ld_stream_float4(p + 4);
+            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
         } else {
-            const double2 a = ld_stream_double2(p), b = ld_stream_double2(p + 2);
-            v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+#pragma unroll
+            for (int k = 0; k < ST_E; k += 2) {
+                const double2 a = ld_stream_double2(p + k);
+                v[k] = a.x, v[k + 1] = a.y;
+            }
         }
     }
 };
@@ -420,54 +450,81 @@ template <typename VT, typename XT> __device__ __forceinline__ double st_prod(co
 struct StArgs {
     const uint32_t *idx;
     const void *val;
-    const int64_t *ends;
+    const int64_t *binbase;
+    const uint32_t *cstart;
     const int32_t *rowmap;
     int nslab, S, P, NW, slab_bytes;
     int32_t ncols;
 };
 
-// One 128-entry block of a cell: this lane's entries are words `iv` / values `vv`; `ne` of them are real
-// (0: the lane lies beyond the cell's end).  (carry_row, carry_sum) is the open run handed from block to
-// block (all lanes hold the same copy).
+// One 256-entry block of a cell.  This lane's 8 entries are the packed words w[] / values vv (all real or
+// inert when `lv`; the lane lies beyond the cell's end otherwise).  (carry_row, carry_sum) is an open run
+// handed from a scan block to the next block (all lanes hold the same copy).
 template <typename VT, typename XT>
-__device__ __forceinline__ void st_block(const uint4 iv, const StVals<VT> &vv, int ne, const XT *__restrict__ xs,
-                                         double *__restrict__ acc_w, int lane, uint32_t &carry_row, double &carry_sum)
+__device__ __forceinline__ void st_block(const uint32_t (&w)[ST_E], const StVals<VT> &vv, const bool lv,
+                                         const XT *__restrict__ xs, double *__restrict__ acc_w, const int lane,
+                                         uint32_t &carry_row, double &carry_sum)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const bool lv = ne > 0;
     uint32_t hr = ST_NOROW, tr = ST_NOROW;
     double H = 0.0, V = 0.0;
     bool single = true;
     if (lv) {
-        const uint32_t w[ST_E] = {iv.x, iv.y, iv.z, iv.w};
+        // Branch-free: all gathers, products and row comparisons are independent; d[k] becomes the running
+        // sum of the run entry k lies in; a run that ends at k < 7 and did not start at entry 0 is complete
+        // inside this lane and is added to its accumulator -- all loads first, then all stores (the rows of
+        // distinct runs are distinct, in this lane and across the warp).
+        uint32_t r[ST_E];
         double d[ST_E];
 #pragma unroll
         for (int k = 0; k < ST_E; k++) {
-            const bool ok = k < ne;
-            const XT xv = xs[ok ? (w[k] & 0xffffu) : 0u];
-            d[k] = ok ? st_prod<VT, XT>(vv, k, xv) : 0.0;
+            r[k] = w[k] >> 16;
+            d[k] = st_prod<VT, XT>(vv, k, xs[w[k] & 0xffffu]);
         }
-        hr = w[0] >> 16;
-        uint32_t cur = hr;
-        double sum = d[0];
+        bool bnd[ST_E];        // bnd[k]: entry k starts a new run
+        bool inner[ST_E];      // inner[k]: a boundary at or before k
+        bnd[0] = false;
+        inner[0] = false;
+        H = d[0];
 #pragma unroll
         for (int k = 1; k < ST_E; k++) {
-            const uint32_t rk = k < ne ? (w[k] >> 16) : cur;
-            if (rk != cur) {
-                if (single) {
-                    H = sum;  // the lane's first run: may continue the previous lane's
-                    single = false;
-                } else {
-                    acc_w[cur] += sum;  // a run that begins and ends inside this lane
-                }
-                cur = rk;
-                sum = 0.0;
-            }
-            sum += d[k];
+            bnd[k] = r[k] != r[k - 1];
+            inner[k] = inner[k - 1] || bnd[k];
+            if (!bnd[k])
+                d[k] += d[k - 1];
+            if (!inner[k])
+                H = d[k];      // still inside the first run
         }
-        tr = cur;
-        V = sum;
+        single = !inner[ST_E - 1];
+        hr = r[0];
+        tr = r[ST_E - 1];
+        V = d[ST_E - 1];
+        double old[ST_E - 1];
+#pragma unroll
+        for (int k = 1; k < ST_E - 1; k++)          // a run ending at k: bnd[k+1]; not the first run: inner[k]
+            if (bnd[k + 1] && inner[k])
+                old[k] = acc_w[r[k]];
+#pragma unroll
+        for (int k = 1; k < ST_E - 1; k++)
+            if (bnd[k + 1] && inner[k])
+                acc_w[r[k]] = old[k] + d[k];
     }
+    if (!__any_sync(FULL, lv && single)) {
+        // No row fills a whole lane, so a row occupies at most the last run of one lane and the first run of
+        // the next: flush all last runs, then all first runs -- never one address twice in an instruction.
+        if (lane == 0 && carry_row != ST_NOROW)
+            acc_w[carry_row] += carry_sum;   // the run a scan block left open
+        carry_row = ST_NOROW;
+        carry_sum = 0.0;
+        if (lv)
+            acc_w[tr] += V;
+        __syncwarp();
+        if (lv)
+            acc_w[hr] += H;
+        __syncwarp();
+        return;
+    }
+    // Long runs: join the pieces of a run that spans lanes with a segmented inclusive scan over the lanes.
     uint32_t prev_tr = __shfl_up_sync(FULL, tr, 1);
     if (lane == 0)
         prev_tr = carry_row;
@@ -497,6 +554,7 @@ __device__ __forceinline__ void st_block(const uint4 iv, const StVals<VT> &vv, i
         acc_w[tr] += out;   // nobody continues my last run
     carry_row = __shfl_sync(FULL, tr, 31);
     carry_sum = __shfl_sync(FULL, out, 31);
+    __syncwarp();
 }
 
 template <typename VT, typename XT, bool MULTI>
@@ -504,8 +562,9 @@ __global__ void __launch_bounds__(1024, 1)
 k_spmv_stream(StArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ carry)
 {
     extern __shared__ __align__(128) unsigned char st_smem[];
-    unsigned char *xbuf = st_smem;                                                     // [2][slab_bytes]
-    double *acc = reinterpret_cast<double *>(st_smem + 2 * (size_t)a.slab_bytes);      // [NW][P]
+    const size_t xstride = (size_t)a.slab_bytes + 128;                                 // slab + the zero slot
+    unsigned char *xbuf = st_smem;                                                     // [2][xstride]
+    double *acc = reinterpret_cast<double *>(st_smem + 2 * xstride);                   // [NW][P]
     uint64_t *bars = reinterpret_cast<uint64_t *>(acc + (size_t)a.NW * a.P);           // full[2], empty[2]
     uint64_t *full = bars, *empty = bars + 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -517,13 +576,15 @@ k_spmv_stream(StArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (tid < 2)
+        reinterpret_cast<XT *>(xbuf + tid * xstride)[a.S] = XT(0);   // what the inert entries multiply
     __syncthreads();   // the only CTA-wide barrier
-    // CTA g walks the slabs starting at slab g*nslab/G and wraps around: at any moment the CTAs pull
-    // DIFFERENT parts of x out of L2 (all of them reading the same lines in step serialises on single L2 slices)
+    // CTA g walks the slabs starting at slab g*nslab/G and wraps around, so that at any moment the CTAs pull
+    // different parts of x out of L2
     const int slab0 = (int)(((int64_t)blockIdx.x * a.nslab) / gridDim.x);
 
     if (warp == a.NW) {
-        // ---------------- producer: x slab s into buffer s & 1
+        // ---------------- producer: the k-th slab of this CTA's walk into buffer k & 1
         if (lane == 0) {
             for (int k = 0; k < a.nslab; k++) {
                 const int st = k & 1;
@@ -535,7 +596,7 @@ k_spmv_stream(StArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ c
                 const int64_t c0 = (int64_t)s * a.S;
                 const int n = (int)min((int64_t)a.S, (int64_t)a.ncols - c0);
                 const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(XT), b16 = bytes & ~15u;
-                XT *dst = reinterpret_cast<XT *>(xbuf + (size_t)st * a.slab_bytes);
+                XT *dst = reinterpret_cast<XT *>(xbuf + st * xstride);
                 for (int i = (int)(b16 / sizeof(XT)); i < n; i++)   // < 16 bytes that a bulk copy cannot move
                     dst[i] = x[c0 + i];
                 if (b16) {
@@ -557,44 +618,37 @@ k_spmv_stream(StArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ c
     for (int i = lane; i < a.P; i += 32)
         acc_w[i] = 0.0;
     __syncwarp();
-    const int64_t *ends = a.ends + bin * (a.nslab + 1);
-    const uint32_t *idx = a.idx;
-    const VT *val = reinterpret_cast<const VT *>(a.val);
+    const int64_t base = a.binbase[bin];
+    const uint32_t *idx = a.idx + base;
+    const VT *val = reinterpret_cast<const VT *>(a.val) + base;
+    const uint32_t *cst = a.cstart + bin * (a.nslab + 1);
     // bounds of the first cell; the next cell's bounds are fetched one slab ahead
-    int64_t nx0 = ends[slab0], nx1 = ends[slab0 + 1];
+    uint32_t nx0 = cst[slab0], nx1 = cst[slab0 + 1];
     for (int k = 0; k < a.nslab; k++) {
-        const int64_t cstart = (nx0 + 3) & ~(int64_t)3, cend = nx1;
+        const uint32_t c0 = nx0, c1 = nx1;
         {
             int sn = k + 1 + slab0;
             if (sn >= a.nslab)
-                sn -= a.nslab;
-            if (sn >= a.nslab)   // k + 1 == nslab: nothing follows
-                sn = 0;
-            nx0 = ends[sn];
-            nx1 = ends[sn + 1];
+                sn -= a.nslab;   // (k + 1 == nslab wraps to slab0: a harmless extra load)
+            nx0 = cst[sn];
+            nx1 = cst[sn + 1];
         }
         const int st = k & 1;
         st_wait(&full[st], (uint32_t)((k >> 1) & 1));
-        const XT *xs = reinterpret_cast<const XT *>(xbuf + (size_t)st * a.slab_bytes);
+        const XT *xs = reinterpret_cast<const XT *>(xbuf + st * xstride);
         uint32_t carry_row = ST_NOROW;
         double carry_sum = 0.0;
-        for (int64_t base = cstart; base < cend; base += 2 * ST_BLK) {
-            const int64_t pA = base + lane * ST_E, pB = pA + ST_BLK;
-            uint4 iA = make_uint4(0, 0, 0, 0), iB = make_uint4(0, 0, 0, 0);
-            StVals<VT> vA, vB;
-            if (pA < cend) {
-                iA = ld_stream_u4(idx + pA);
-                vA.load(val + pA);
+        for (uint32_t b = c0; b < c1; b += ST_BLK) {
+            const uint32_t p = b + lane * ST_E;
+            const bool lv = p < c1;
+            uint32_t w[ST_E] = {0, 0, 0, 0, 0, 0, 0, 0};
+            StVals<VT> vv;
+            if (lv) {
+                const uint4 q0 = ld_stream_u4(idx + p), q1 = ld_stream_u4(idx + p + 4);
+                w[0] = q0.x, w[1] = q0.y, w[2] = q0.z, w[3] = q0.w, w[4] = q1.x, w[5] = q1.y, w[6] = q1.z, w[7] = q1.w;
+                vv.load(val + p);
             }
-            if (pB < cend) {
-                iB = ld_stream_u4(idx + pB);
-                vB.load(val + pB);
-            }
-            st_block<VT, XT>(iA, vA, (int)max((int64_t)0, min((int64_t)ST_E, cend - pA)), xs, acc_w, lane, carry_row,
-                             carry_sum);
-            if (base + ST_BLK < cend)
-                st_block<VT, XT>(iB, vB, (int)max((int64_t)0, min((int64_t)ST_E, cend - pB)), xs, acc_w, lane, carry_row,
-                                 carry_sum);
+            st_block<VT, XT>(w, vv, lv, xs, acc_w, lane, carry_row, carry_sum);
         }
         if (lane == 0 && carry_row != ST_NOROW)
             acc_w[carry_row] += carry_sum;
@@ -663,7 +717,8 @@ int stream_run(csrk_matrix *h, StreamPlan *P, const void *d_x, const YOut &y, cu
     StArgs a;
     a.idx = P->idx;
     a.val = P->val;
-    a.ends = P->ends;
+    a.binbase = P->binbase;
+    a.cstart = P->cstart;
     a.rowmap = P->rowmap;
     a.nslab = P->nslab;
     a.S = P->S;
