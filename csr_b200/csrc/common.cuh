@@ -132,7 +132,10 @@ struct Options {
     std::atomic<int64_t> stream_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a stream plan
     std::atomic<int64_t> stream_slab_bytes{0};          // > 0: cap on the x slab size (tests force many slabs)
     std::atomic<int64_t> stream_ctas{0};                // > 0: CTAs (row groups) of the stream kernel instead of one per SM
-    std::atomic<int64_t> stream_warps{31};              // consumer warps per CTA of the stream kernel (1..31)
+    std::atomic<int64_t> stream_warps{16};              // consumer warps per CTA of the stream kernel (1..31)
+    std::atomic<int64_t> stream_piece{512};             // longest pseudo-row: longer rows are cut into interleaved pieces
+    std::atomic<int64_t> stream_ring_bytes{4096};       // per-warp prefetch ring of the entry stream (4096 | 8192)
+    std::atomic<int64_t> stream_ring_chunks{4};         // chunks (bulk copies) per ring: 2 | 4
     std::atomic<int64_t> radix_bits{0};                 // digit width of the stable sort: 0 = pick (9 when it saves a pass), 8, 9
     std::atomic<int64_t> spmv_zero_copy_y{1};           // csrk_spmv: store rows straight into pinned host y
     std::atomic<int64_t> fix_threads{1024};             // threads per CTA of the fixed-point SpGEMM kernel (512 | 768 | 1024)
@@ -174,7 +177,7 @@ int from_coo_run(int32_t nrows, int32_t ncols, int64_t nnz, const int32_t *d_row
 void stream_destroy(StreamPlan *p, cudaStream_t s);
 int stream_build(csrk_matrix *h, int x_kind, StreamPlan **out, cudaStream_t s);  // syncs internally; CSRK_EOVERFLOW = not representable
 int stream_run(csrk_matrix *h, StreamPlan *p, const void *d_x, const YOut &y, cudaStream_t s);
-void stream_info(const StreamPlan *p, int64_t *out /*[8]: G, NW, nslab, S, P, Q, n_split, smem*/);
+void stream_info(const StreamPlan *p, int64_t *out /*[11]: G, NW, nslab, S, P, Q, n_split, smem, stream bytes, piece, ring*/);
 
 // ops implemented across the .cu files (all enqueue on `s`, no sync unless stated)
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s);

@@ -381,6 +381,15 @@ int csrk_set_option(const char *name, int64_t value)
     } else if (!strcmp(name, "stream_warps")) {
         CSRK_ARG(value >= 1 && value <= 31, "stream_warps must be 1..31");
         options().stream_warps = value;
+    } else if (!strcmp(name, "stream_piece")) {
+        CSRK_ARG(value >= 8 && value <= 4096, "stream_piece must be 8..4096");
+        options().stream_piece = value;
+    } else if (!strcmp(name, "stream_ring_bytes")) {
+        CSRK_ARG(value == 4096 || value == 8192, "stream_ring_bytes must be 4096 or 8192");
+        options().stream_ring_bytes = value;
+    } else if (!strcmp(name, "stream_ring_chunks")) {
+        CSRK_ARG(value == 2 || value == 4, "stream_ring_chunks must be 2 or 4");
+        options().stream_ring_chunks = value;
     } else if (!strcmp(name, "radix_bits")) {
         CSRK_ARG(value == 0 || value == 8 || value == 9, "radix_bits must be 0, 8 or 9");
         options().radix_bits = value;
@@ -596,11 +605,11 @@ int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stre
     return spmv_run(h, d_x, x_kind, d_y, s);
 }
 
-int csrk_spmv_plan_info(csrk_h h, int x_kind, int64_t info[9])
+int csrk_spmv_plan_info(csrk_h h, int x_kind, int64_t info[12])
 {
     CSRK_ARG(h != nullptr && info != nullptr, "NULL argument");
     CSRK_ARG(x_kind == 4 || x_kind == 8, "x_kind must be 4 or 8 (got %d)", x_kind);
-    for (int i = 0; i < 9; i++)
+    for (int i = 0; i < 12; i++)
         info[i] = 0;
     std::lock_guard<std::mutex> g(h->mu);
     if (StreamPlan *p = h->stream[x_kind == 4 ? 0 : 1]) {

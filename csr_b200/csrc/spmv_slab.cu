@@ -1,0 +1,953 @@
+// spmv_slab.cu -- mult_vec (csr/kernels/numba/__init__.py:55-67) for matrices whose x does not fit L1:
+// the slab kernel with run-packed entry streams.
+//
+// Why.  The CSR tile kernel (spmv.cu) gathers x through L1/L2: with columns spread over an x of several
+// MB every 4-byte gather costs one 32-byte L2 sector, 5x the bytes of the (colind, value) stream itself,
+// and the kernel sits on the L2->SM fabric at a third of the HBM roofline (profiles/r01_spmv_tile_ncu.md).
+// Here x is staged in SHARED memory, slab by slab, and the entries are re-laid out ONCE per handle:
+//
+//   * x is cut into slabs of S columns; one persistent CTA per SM keeps two slabs in shared memory, a
+//     producer warp fetching the next slab with cp.async.bulk (TMA) + mbarriers while the consumer warps
+//     work on the current one.  The gathers become LDS.
+//   * rows longer than `piece` entries are cut into interleaved pieces (piece j = entries j, j+n, j+2n, ...
+//     so that every piece spans the row's whole column range); the pieces ("pseudo-rows") are sorted by
+//     length and dealt to G*NW bins (one bin per consumer WARP) in snake order: every warp owns the same
+//     number of pseudo-rows with the same mix of lengths.  No dynamic scheduling, no inter-warp
+//     communication, no CTA-wide barrier in the whole kernel; every pseudo-row has one float64 accumulator
+//     in its warp's private part of shared memory.
+//   * a warp's entries in one slab form a CELL.  Inside a cell the entries of one pseudo-row are a RUN.
+//     Runs of two or more entries are sorted by length and packed 32 at a time into J GROUPS: lane l owns
+//     run l, step t of the group holds entry t of every run that is longer than t, stored contiguously
+//     (jagged-diagonal order).  A lane sums its run in a register -- no row tracking, no cross-lane
+//     reduction -- and adds it to the accumulator with one plain read-modify-write (the 32 runs of a
+//     group belong to 32 different pseudo-rows).  Groups are cut every 8 steps so that a group is at most
+//     a few KB.  Runs of exactly one entry go, 32 at a time, into L GROUPS: one read-modify-write per
+//     entry, again 32 distinct rows per instruction.  No atomics anywhere: results are deterministic.
+//   * J entries cost 2 + V bytes (16-bit column inside the slab, value; the row lives in the group header),
+//     L entries 4 + V (row << 16 | column): the stream is smaller than the CSR arrays it replaces.
+//   * every warp's stream is ONE contiguous byte sequence in the order the warp consumes it (cell header,
+//     J groups, L groups; cells in the CTA's slab walk order), and the warp itself prefetches it into a
+//     private shared-memory ring with cp.async.bulk, several chunks ahead: HBM latency is hidden by the
+//     ring, not by occupancy, and the loop never waits for a global load.
+//   * pieces of split rows go to a carry array and a tiny fix-up kernel adds them in piece order.
+//
+// Cost model: HBM bytes are the stream + x once + y; the L2->SM fabric carries the stream
+// plus G copies of x, which is why auto mode only picks this kernel when G*ncols*X is below the stream size.
+#include <type_traits>
+
+#include "expand.cuh"
+#include "radix.cuh"
+#include "spmv.cuh"
+
+namespace csrk {
+
+constexpr int SL_TB = 8;                   // steps per J group
+constexpr int SL_HDR = 144;                // J group header: 32 x (row << 16 | len), n, T, 0, 0
+constexpr int SL_NST_MAX = 4;              // chunks per ring: 2 or 4
+constexpr int SL_MAX_WARPS = 31;           // consumer warps (+1 producer warp = 1024 threads)
+
+struct StreamPlan {
+    int G = 0, NW = 0, nslab = 0, S = 0, P = 0, x_kind = 0, piece = 0, ring = 0, nst = 4;
+    int slab_bytes = 0;
+    size_t smem_bytes = 0;
+    int64_t Q = 0, stream_bytes = 0;
+    int n_split = 0;
+    unsigned char *stream = nullptr;  // all bins' byte streams, bin after bin
+    int64_t *binbase = nullptr;       // [G*NW] start of bin b's stream
+    uint32_t *binlen = nullptr;       // [G*NW] its length (bytes, multiple of 16)
+    int32_t *rowmap = nullptr;        // [G*NW][P]: >= 0 row of y, -1 unused, <= -2 carry slot -(v+2)
+    int32_t *split = nullptr;         // [3*n_split]: row, first carry slot, number of pieces
+};
+
+void stream_destroy(StreamPlan *p, cudaStream_t s)
+{
+    if (!p)
+        return;
+    dev_free(p->stream, s);
+    dev_free(p->binbase, s);
+    dev_free(p->binlen, s);
+    dev_free(p->rowmap, s);
+    dev_free(p->split, s);
+    delete p;
+}
+
+__host__ __device__ __forceinline__ uint32_t sl_pad16(uint32_t b) { return (b + 15u) & ~15u; }
+
+// ------------------------------------------------------------------ plan builder
+template <typename RPT> struct SlPieceLoader {
+    const RPT *rp;
+    int piece;
+    __device__ __forceinline__ int64_t operator()(int64_t r) const
+    {
+        const int64_t len = (int64_t)rp[r + 1] - (int64_t)rp[r];
+        return len > piece ? (len + piece - 1) / piece : 1;
+    }
+};
+
+// one thread per row: sort key (piece - length: longest first), id and y destination of each piece
+template <typename RPT>
+__global__ void k_sl_pieces(const RPT *__restrict__ rp, int32_t nrows, int piece, const int64_t *__restrict__ qbase,
+                            int32_t *__restrict__ qkey, int32_t *__restrict__ qid, int32_t *__restrict__ qdest,
+                            int32_t *__restrict__ split, int *__restrict__ split_cnt)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows)
+        return;
+    const int64_t len = (int64_t)rp[r + 1] - (int64_t)rp[r];
+    const int64_t q0 = qbase[r], nq = qbase[r + 1] - q0;
+    for (int64_t j = 0; j < nq; j++) {
+        const int64_t l = (len - j + nq - 1) / nq;   // piece j = entries j, j+nq, j+2nq, ... of the row
+        qkey[q0 + j] = (int32_t)(piece - l);
+        qid[q0 + j] = (int32_t)(q0 + j);
+        qdest[q0 + j] = nq == 1 ? (int32_t)r : -(int32_t)(q0 + j) - 2;
+    }
+    if (nq > 1) {
+        const int k = atomicAdd(split_cnt, 1);
+        split[3 * k] = (int32_t)r;
+        split[3 * k + 1] = (int32_t)q0;
+        split[3 * k + 2] = (int32_t)nq;
+    }
+}
+
+// sorted position j -> bin (snake order over the B bins) and local row j / B
+__global__ void k_sl_deal(const int32_t *__restrict__ order, const int32_t *__restrict__ qdest, int64_t Q, int B, int P,
+                          int32_t *__restrict__ qbl, int32_t *__restrict__ rowmap)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Q)
+        return;
+    const int q = order[j];
+    const int round = (int)(j / B), k = (int)(j % B);
+    const int bin = (round & 1) ? B - 1 - k : k;
+    qbl[q] = bin << 16 | round;
+    rowmap[(int64_t)bin * P + round] = qdest[q];
+}
+
+__global__ void k_sl_fill_i32(int32_t *p, int64_t n, int32_t v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        p[i] = v;
+}
+
+// Sort input, in PIECE-MAJOR order: position e' of row r's range is entry i of piece j (the pieces of a row
+// one after the other), which is entry t = i*nq + j of the row.  Piece-major order keeps the entries of a
+// pseudo-row adjacent inside every cell after the stable sort, whatever the column order inside the row.
+// key = bin*nslab + (position of the slab in the CTA's walk), packed = local row << 16 | column inside the
+// slab, pval = the entry's value.
+template <typename RPT, typename VT>
+__global__ void k_sl_keys(const RPT *__restrict__ rp, const int32_t *__restrict__ ci, const VT *__restrict__ vs,
+                          const int32_t *__restrict__ rows, int64_t nnz, const int64_t *__restrict__ qbase,
+                          const int32_t *__restrict__ qbl, int S, int nslab, int G, int NW, int32_t *__restrict__ key,
+                          int32_t *__restrict__ packed, VT *__restrict__ pval)
+{
+    const int64_t ep = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ep >= nnz)
+        return;
+    const int32_t r = rows[ep];
+    const int64_t r0 = (int64_t)rp[r], len = (int64_t)rp[r + 1] - r0;
+    const int64_t u = ep - r0;
+    const int64_t q0 = qbase[r], nq = qbase[r + 1] - q0;
+    int64_t j = 0, t = u;
+    if (nq > 1) {
+        const int64_t f = len / nq, m = len % nq;   // the first m pieces hold f+1 entries, the others f
+        int64_t i;
+        if (u < m * (f + 1)) {
+            j = u / (f + 1);
+            i = u % (f + 1);
+        } else {
+            const int64_t v = u - m * (f + 1);
+            j = m + v / f;
+            i = v % f;
+        }
+        t = i * nq + j;
+    }
+    const int64_t e = r0 + t;
+    const int32_t bl = qbl[q0 + j];
+    const int32_t c = ci[e];
+    const int slab = c / S;
+    const int bin = bl >> 16;
+    int walk = slab - (int)(((int64_t)(bin / NW) * nslab) / G);   // the CTA starts its walk at slab g*nslab/G
+    if (walk < 0)
+        walk += nslab;
+    key[ep] = bin * nslab + walk;
+    packed[ep] = (int32_t)(((uint32_t)(bl & 0xffff) << 16) | (uint32_t)(c - slab * S));
+    if constexpr (!std::is_same<VT, NoPayload>::value)
+        pval[ep] = vs[e];
+}
+
+// 1 where a run starts: first entry, new cell, or new pseudo-row
+struct SlRunFlag {
+    const int32_t *k, *p;
+    __device__ __forceinline__ int32_t operator()(int64_t i) const
+    {
+        return (i == 0 || k[i] != k[i - 1] || ((uint32_t)p[i] >> 16) != ((uint32_t)p[i - 1] >> 16)) ? 1 : 0;
+    }
+};
+
+__global__ void k_sl_run_starts(SlRunFlag f, const int32_t *__restrict__ ex, int64_t nnz, int32_t *__restrict__ rs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nnz)
+        return;
+    if (i == nnz)
+        rs[ex[nnz]] = (int32_t)nnz;
+    else if (f(i))
+        rs[ex[i]] = (int32_t)i;
+}
+
+// run -> sort key: cell, then longest first (runs of one entry end up last in their cell)
+__global__ void k_sl_run_keys(const int32_t *__restrict__ rs, const int32_t *__restrict__ skeys, int32_t NR, int LB,
+                              int32_t *__restrict__ rkey, int32_t *__restrict__ rid)
+{
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= NR)
+        return;
+    const int32_t len = rs[r + 1] - rs[r];
+    const int32_t lmax = (1 << LB) - 1;
+    rkey[r] = (skeys[rs[r]] << LB) | (lmax - len);
+    rid[r] = r;
+}
+
+// sorted runs -> (cell*2 + (len == 1)) for the segment bounds, and the length itself
+__global__ void k_sl_run_class(const int32_t *__restrict__ srkey, int32_t NR, int LB, int32_t *__restrict__ k3,
+                               int32_t *__restrict__ slen)
+{
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= NR)
+        return;
+    const int32_t lmax = (1 << LB) - 1;
+    const int32_t len = lmax - (srkey[j] & lmax);
+    slen[j] = len;
+    k3[j] = ((srkey[j] >> LB) << 1) | (len == 1 ? 1 : 0);
+}
+
+// items of a cell: 1 header + J groups (32 runs each, all their steps) + L groups (32 one-entry runs each)
+struct SlItemCount {
+    const int32_t *b;   // [2*ncells+1]
+    __device__ __forceinline__ int64_t operator()(int64_t c) const
+    {
+        const int32_t nj = b[2 * c + 1] - b[2 * c], nl = b[2 * c + 2] - b[2 * c + 1];
+        return 1 + (nj + 31) / 32 + (nl + 31) / 32;
+    }
+};
+
+struct SlItem {
+    int64_t cell;
+    int kind;        // 0 header, 1 J group, 2 L group
+    int32_t j0, j1;  // sorted-run range of the group
+};
+__device__ __forceinline__ SlItem sl_decode(int64_t item, const int64_t *__restrict__ itembase, int64_t ncells,
+                                            const int32_t *__restrict__ b)
+{
+    int64_t lo = 0, hi = ncells;   // largest c with itembase[c] <= item
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (itembase[mid] <= item)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    SlItem it;
+    it.cell = lo;
+    const int local = (int)(item - itembase[lo]);
+    const int32_t bj = b[2 * lo], bl = b[2 * lo + 1], be = b[2 * lo + 2];
+    const int njg = (bl - bj + 31) / 32;
+    if (local == 0) {
+        it.kind = 0;
+        it.j0 = it.j1 = 0;
+    } else if (local <= njg) {
+        it.kind = 1;
+        it.j0 = bj + 32 * (local - 1);
+        it.j1 = min(it.j0 + 32, bl);
+    } else {
+        it.kind = 2;
+        it.j0 = bl + 32 * (local - 1 - njg);
+        it.j1 = min(it.j0 + 32, be);
+    }
+    return it;
+}
+
+// one warp per item: its size in the stream; J groups also count their 8-step sub-groups into the cell
+template <int VB>
+__global__ void __launch_bounds__(256)
+k_sl_item_bytes(int64_t NI, const int64_t *__restrict__ itembase, int64_t ncells, const int32_t *__restrict__ b,
+                const int32_t *__restrict__ slen, uint32_t *__restrict__ itembytes, int32_t *__restrict__ cellsub)
+{
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= NI)
+        return;
+    const SlItem it = sl_decode(item, itembase, ncells, b);
+    uint32_t bytes;
+    if (it.kind == 0) {
+        bytes = 16;
+    } else if (it.kind == 2) {
+        bytes = 128 + 32 * VB;
+    } else {
+        const int32_t len = it.j0 + lane < it.j1 ? slen[it.j0 + lane] : 0;
+        const int32_t T = __shfl_sync(0xffffffffu, len, 0);
+        bytes = 0;
+        int nsub = 0;
+        for (int t0 = 0; t0 < T; t0 += SL_TB, nsub++) {
+            const int n = warp_sum(min(max(len - t0, 0), SL_TB));
+            bytes += SL_HDR + sl_pad16(2u * n) + sl_pad16((uint32_t)VB * n);
+        }
+        if (lane == 0)
+            atomicAdd(&cellsub[it.cell], nsub);
+    }
+    if (lane == 0)
+        itembytes[item] = bytes;
+}
+
+// one warp per item: write it
+template <typename VT>
+__global__ void __launch_bounds__(256)
+k_sl_fill(int64_t NI, const int64_t *__restrict__ itembase, int64_t ncells, const int32_t *__restrict__ b,
+          const int32_t *__restrict__ slen, const int32_t *__restrict__ srid, const int32_t *__restrict__ rs,
+          const int32_t *__restrict__ spacked, const VT *__restrict__ svals, const int64_t *__restrict__ itemoff,
+          const int32_t *__restrict__ cellsub, unsigned char *__restrict__ stream, int P, int S)
+{
+    constexpr int VB = std::is_same<VT, NoPayload>::value ? 0 : (int)sizeof(VT);
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= NI)
+        return;
+    const SlItem it = sl_decode(item, itembase, ncells, b);
+    unsigned char *o = stream + itemoff[item];
+    if (it.kind == 0) {
+        if (lane == 0) {
+            const int32_t bj = b[2 * it.cell], bl = b[2 * it.cell + 1], be = b[2 * it.cell + 2];
+            (void)bj;
+            *reinterpret_cast<uint4 *>(o) = make_uint4((uint32_t)cellsub[it.cell], (uint32_t)((be - bl + 31) / 32), 0u, 0u);
+        }
+        return;
+    }
+    const bool have = it.j0 + lane < it.j1;
+    const int32_t start = have ? rs[srid[it.j0 + lane]] : 0;
+    if (it.kind == 2) {
+        // one-entry runs; unused lanes are inert: dummy accumulator P, the always-zero x slot S, value 0
+        reinterpret_cast<uint32_t *>(o)[lane] = have ? (uint32_t)spacked[start] : ((uint32_t)P << 16 | (uint32_t)S);
+        if constexpr (VB > 0)
+            reinterpret_cast<VT *>(o + 128)[lane] = have ? svals[start] : VT(0);
+        return;
+    }
+    const int32_t len = have ? slen[it.j0 + lane] : 0;
+    const uint32_t row = have ? ((uint32_t)spacked[start] >> 16) : (uint32_t)P;
+    const int32_t T = __shfl_sync(0xffffffffu, len, 0);
+    for (int t0 = 0; t0 < T; t0 += SL_TB) {
+        const int lk = min(max(len - t0, 0), SL_TB);
+        const int Tk = min(T - t0, SL_TB);
+        const int n = warp_sum(lk);
+        reinterpret_cast<uint32_t *>(o)[lane] = row << 16 | (uint32_t)Tk << 8 | (uint32_t)lk;
+        uint16_t *offs = reinterpret_cast<uint16_t *>(o + 128);   // entries before step 1..7, then n
+        uint16_t *cols = reinterpret_cast<uint16_t *>(o + SL_HDR);
+        unsigned char *vals = o + SL_HDR + sl_pad16(2u * n);
+        int off = 0;
+        for (int t = 0; t < SL_TB; t++) {
+            const bool act = t < lk;
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const int32_t src = start + t0 + t;
+                cols[off + lane] = (uint16_t)((uint32_t)spacked[src] & 0xffffu);
+                if constexpr (VB > 0)
+                    reinterpret_cast<VT *>(vals)[off + lane] = svals[src];
+            }
+            off += __popc(bal);
+            if (lane == 0)
+                offs[t] = (uint16_t)off;   // offs[7] = n
+        }
+        o += SL_HDR + sl_pad16(2u * n) + sl_pad16((uint32_t)VB * n);
+    }
+}
+
+__global__ void k_sl_bins(const int64_t *__restrict__ itembase, const int64_t *__restrict__ itemoff, int B, int nslab,
+                          int64_t *__restrict__ binbase, uint32_t *__restrict__ binlen)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B)
+        return;
+    const int64_t o0 = itemoff[itembase[(int64_t)b * nslab]], o1 = itemoff[itembase[(int64_t)(b + 1) * nslab]];
+    binbase[b] = o0;
+    binlen[b] = (uint32_t)(o1 - o0);
+}
+
+static int sl_bits(int64_t n)
+{
+    int b = 1;
+    while (((int64_t)1 << b) < n)
+        b++;
+    return b;
+}
+
+template <typename RPT, typename VT>
+static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
+{
+    constexpr bool HASV = !std::is_same<VT, NoPayload>::value;
+    constexpr int VB = HASV ? (int)sizeof(VT) : 0;
+    const RPT *rp = (const RPT *)h->rp;
+    const int32_t nrows = h->nrows;
+    const int64_t nnz = h->nnz;
+    const int B = P->G * P->NW;
+    if (nnz >= ((int64_t)1 << 31) - 64)
+        return CSRK_EOVERFLOW;   // run starts and run ids are 32-bit
+
+    // 1. pseudo-rows
+    DevBuf qbase;
+    CSRK_TRY(qbase.alloc(sizeof(int64_t) * ((size_t)nrows + 1), s));
+    CSRK_TRY((exclusive_scan<int64_t>(SlPieceLoader<RPT>{rp, P->piece}, (int64_t)nrows, qbase.as<int64_t>(), s)));
+    int64_t Q = 0;
+    CSRK_CUDA(cudaMemcpyAsync(&Q, qbase.as<int64_t>() + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    P->Q = Q;
+    P->P = (int)std::max<int64_t>(div_up(Q, B), 1);
+    // shared memory: NW rings + NW*(P+1) float64 accumulators + mbarriers + two x slabs
+    const size_t acc_bytes = (size_t)P->NW * (P->P + 1) * 8;
+    const size_t ring_bytes = (size_t)P->NW * P->ring;
+    const size_t bar_bytes = (size_t)(4 + P->NW * SL_NST_MAX) * 8;
+    const size_t smem_max = ctx().smem_optin;
+    if (P->P > 65534 || Q >= ((int64_t)1 << 31) || acc_bytes + ring_bytes + bar_bytes + 2 * 4096 > smem_max)
+        return CSRK_EOVERFLOW;  // too many rows for shared-memory accumulators: stay on the tile kernel
+    // a buffer is one slab + 128 bytes (the always-zero slot the inert entries point at)
+    int64_t slab = (int64_t)((smem_max - acc_bytes - ring_bytes - bar_bytes) / 2 - 128) & ~(int64_t)127;
+    slab = std::min<int64_t>(slab, (int64_t)65408 * P->x_kind);   // columns inside a slab (and the zero slot) fit 16 bits
+    slab = std::min<int64_t>(slab, (((int64_t)h->ncols * P->x_kind) + 127) & ~(int64_t)127);
+    const int64_t cap = options().stream_slab_bytes.load();
+    if (cap > 0)
+        slab = std::min<int64_t>(slab, std::max<int64_t>(cap & ~(int64_t)127, 128));
+    slab = std::max<int64_t>(slab, 128);
+    P->slab_bytes = (int)slab;
+    P->S = (int)(slab / P->x_kind);
+    P->nslab = (int)std::max<int64_t>(div_up((int64_t)h->ncols, P->S), 1);
+    P->smem_bytes = ring_bytes + 2 * ((size_t)slab + 128) + acc_bytes + bar_bytes;
+    const int64_t ncells = (int64_t)B * P->nslab;
+    const int LB = sl_bits((int64_t)P->piece + 2);   // run lengths 1..piece (duplicate columns may exceed S)
+    if (ncells >= ((int64_t)1 << (30 - LB)))
+        return CSRK_EOVERFLOW;   // (cell, length) run keys are 31-bit
+
+    DevBuf qkey, qid, qdest, order, qbl, splitcnt;
+    CSRK_TRY(qkey.alloc(sizeof(int32_t) * (size_t)Q, s));
+    CSRK_TRY(qid.alloc(sizeof(int32_t) * (size_t)Q, s));
+    CSRK_TRY(qdest.alloc(sizeof(int32_t) * (size_t)Q, s));
+    CSRK_TRY(order.alloc(sizeof(int32_t) * (size_t)Q, s));
+    CSRK_TRY(qbl.alloc(sizeof(int32_t) * (size_t)Q, s));
+    CSRK_TRY(splitcnt.alloc_zero(sizeof(int), s));
+    const int64_t max_split = nnz / P->piece + 1;
+    CSRK_TRY(dev_alloc((void **)&P->split, sizeof(int32_t) * 3 * (size_t)max_split, s));
+    CSRK_LAUNCH((k_sl_pieces<RPT>), (unsigned)div_up((int64_t)nrows, 256), 256, 0, s, rp, nrows, P->piece,
+                qbase.as<int64_t>(), qkey.as<int32_t>(), qid.as<int32_t>(), qdest.as<int32_t>(), P->split,
+                splitcnt.as<int>());
+    // 2. longest first (stable), dealt to the bins in snake order
+    CSRK_TRY((radix_sort_by_key<NoPayload>(qkey.as<int32_t>(), qid.as<int32_t>(), (const NoPayload *)nullptr, Q,
+                                           sl_bits((int64_t)P->piece + 1), order.as<int32_t>(), (NoPayload *)nullptr, s)));
+    CSRK_TRY(dev_alloc((void **)&P->rowmap, sizeof(int32_t) * (size_t)B * P->P, s));
+    CSRK_LAUNCH(k_sl_fill_i32, (unsigned)div_up((int64_t)B * P->P, 256), 256, 0, s, P->rowmap, (int64_t)B * P->P, -1);
+    CSRK_LAUNCH(k_sl_deal, (unsigned)div_up(Q, 256), 256, 0, s, order.as<int32_t>(), qdest.as<int32_t>(), Q, B, P->P,
+                qbl.as<int32_t>(), P->rowmap);
+    CSRK_TRACE_MARK("slab plan: pieces dealt", s);
+
+    // 3. entries: key = (bin, slab in walk order), stable sort keeps the runs together
+    DevBuf rows, key, packed, pval, skeys, spacked, svals;
+    CSRK_TRY(rows.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    CSRK_TRY(key.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    CSRK_TRY(packed.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    if (HASV)
+        CSRK_TRY(pval.alloc(sizeof(VT) * (size_t)nnz, s));
+    CSRK_LAUNCH((k_expand_rows<RPT>), (unsigned)div_up(nnz, EXP_TILE), 256, 0, s, rp, nrows, nnz, rows.as<int32_t>());
+    CSRK_LAUNCH((k_sl_keys<RPT, VT>), (unsigned)div_up(nnz, 256), 256, 0, s, rp, h->ci, (const VT *)h->vs,
+                rows.as<int32_t>(), nnz, qbase.as<int64_t>(), qbl.as<int32_t>(), P->S, P->nslab, P->G, P->NW,
+                key.as<int32_t>(), packed.as<int32_t>(), HASV ? pval.as<VT>() : nullptr);
+    CSRK_TRY(skeys.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    CSRK_TRY(spacked.alloc(sizeof(int32_t) * (size_t)nnz, s));
+    if (HASV)
+        CSRK_TRY(svals.alloc(sizeof(VT) * (size_t)nnz, s));
+    CSRK_TRY((radix_sort_by_key<VT>(key.as<int32_t>(), packed.as<int32_t>(), HASV ? pval.as<VT>() : nullptr, nnz,
+                                    sl_bits(ncells), spacked.as<int32_t>(), HASV ? svals.as<VT>() : nullptr, s,
+                                    skeys.as<int32_t>())));
+    CSRK_TRACE_MARK("slab plan: entries sorted", s);
+
+    // 4. runs: starts, lengths, sorted by (cell, longest first)
+    DevBuf ex, rs;
+    CSRK_TRY(ex.alloc(sizeof(int32_t) * ((size_t)nnz + 1), s));
+    const SlRunFlag flag{skeys.as<int32_t>(), spacked.as<int32_t>()};
+    CSRK_TRY((exclusive_scan<int32_t>(flag, nnz, ex.as<int32_t>(), s)));
+    int32_t NR = 0;
+    CSRK_CUDA(cudaMemcpyAsync(&NR, ex.as<int32_t>() + nnz, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    CSRK_TRY(rs.alloc(sizeof(int32_t) * ((size_t)NR + 1), s));
+    CSRK_LAUNCH(k_sl_run_starts, (unsigned)div_up(nnz + 1, 256), 256, 0, s, flag, ex.as<int32_t>(), nnz, rs.as<int32_t>());
+    DevBuf rkey, rid, srkey, srid, k3, slen, bnd;
+    CSRK_TRY(rkey.alloc(sizeof(int32_t) * (size_t)NR, s));
+    CSRK_TRY(rid.alloc(sizeof(int32_t) * (size_t)NR, s));
+    CSRK_TRY(srkey.alloc(sizeof(int32_t) * (size_t)NR, s));
+    CSRK_TRY(srid.alloc(sizeof(int32_t) * (size_t)NR, s));
+    CSRK_LAUNCH(k_sl_run_keys, (unsigned)div_up((int64_t)NR, 256), 256, 0, s, rs.as<int32_t>(), skeys.as<int32_t>(), NR, LB,
+                rkey.as<int32_t>(), rid.as<int32_t>());
+    CSRK_TRY((radix_sort_by_key<NoPayload>(rkey.as<int32_t>(), rid.as<int32_t>(), (const NoPayload *)nullptr, (int64_t)NR,
+                                           sl_bits(ncells) + LB, srid.as<int32_t>(), (NoPayload *)nullptr, s,
+                                           srkey.as<int32_t>())));
+    CSRK_TRY(k3.alloc(sizeof(int32_t) * (size_t)NR, s));
+    CSRK_TRY(slen.alloc(sizeof(int32_t) * (size_t)NR, s));
+    CSRK_LAUNCH(k_sl_run_class, (unsigned)div_up((int64_t)NR, 256), 256, 0, s, srkey.as<int32_t>(), NR, LB, k3.as<int32_t>(),
+                slen.as<int32_t>());
+    CSRK_TRY(bnd.alloc(sizeof(int32_t) * (2 * (size_t)ncells + 1), s));
+    CSRK_LAUNCH((k_key_bounds<int32_t>), (unsigned)div_up(div_up((int64_t)NR + 1, 4), 256), 256, 0, s, k3.as<int32_t>(),
+                (int64_t)NR, (int32_t)(2 * ncells), bnd.as<int32_t>());
+    CSRK_TRACE_MARK("slab plan: runs sorted", s);
+
+    // 5. items (cell headers and groups): sizes, offsets, contents
+    DevBuf itembase, itembytes, itemoff, cellsub;
+    CSRK_TRY(itembase.alloc(sizeof(int64_t) * ((size_t)ncells + 1), s));
+    CSRK_TRY((exclusive_scan<int64_t>(SlItemCount{bnd.as<int32_t>()}, ncells, itembase.as<int64_t>(), s)));
+    int64_t NI = 0;
+    CSRK_CUDA(cudaMemcpyAsync(&NI, itembase.as<int64_t>() + ncells, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    CSRK_TRY(itembytes.alloc(sizeof(uint32_t) * (size_t)NI, s));
+    CSRK_TRY(itemoff.alloc(sizeof(int64_t) * ((size_t)NI + 1), s));
+    CSRK_TRY(cellsub.alloc_zero(sizeof(int32_t) * (size_t)ncells, s));
+    CSRK_LAUNCH((k_sl_item_bytes<VB>), (unsigned)div_up(NI * 32, 256), 256, 0, s, NI, itembase.as<int64_t>(), ncells,
+                bnd.as<int32_t>(), slen.as<int32_t>(), itembytes.as<uint32_t>(), cellsub.as<int32_t>());
+    CSRK_TRY((exclusive_scan<int64_t>(ArrayLoader<uint32_t>{itembytes.as<uint32_t>()}, NI, itemoff.as<int64_t>(), s)));
+    int64_t total = 0;
+    CSRK_CUDA(cudaMemcpyAsync(&total, itemoff.as<int64_t>() + NI, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    P->stream_bytes = total;
+    // (the ring prefetch reads whole chunks: the last bin's final chunk may run past its stream)
+    CSRK_TRY(dev_alloc((void **)&P->stream, (size_t)total + (size_t)P->ring, s));
+    CSRK_TRY(dev_alloc((void **)&P->binbase, sizeof(int64_t) * (size_t)B, s));
+    CSRK_TRY(dev_alloc((void **)&P->binlen, sizeof(uint32_t) * (size_t)B, s));
+    CSRK_LAUNCH((k_sl_fill<VT>), (unsigned)div_up(NI * 32, 256), 256, 0, s, NI, itembase.as<int64_t>(), ncells,
+                bnd.as<int32_t>(), slen.as<int32_t>(), srid.as<int32_t>(), rs.as<int32_t>(), spacked.as<int32_t>(),
+                HASV ? svals.as<VT>() : nullptr, itemoff.as<int64_t>(), cellsub.as<int32_t>(), P->stream, P->P, P->S);
+    CSRK_LAUNCH(k_sl_bins, (unsigned)div_up(B, 256), 256, 0, s, itembase.as<int64_t>(), itemoff.as<int64_t>(), B, P->nslab,
+                P->binbase, P->binlen);
+    CSRK_CUDA(cudaMemcpyAsync(&P->n_split, splitcnt.as<int>(), sizeof(int), cudaMemcpyDeviceToHost, s));
+    CSRK_CUDA(cudaStreamSynchronize(s));
+    if (total / B + P->ring >= ((int64_t)1 << 31))
+        return CSRK_EOVERFLOW;   // positions inside a bin's stream are 32-bit
+    CSRK_TRACE_MARK("slab plan: streams written", s);
+    return CSRK_OK;
+}
+
+int stream_build(csrk_matrix *h, int x_kind, StreamPlan **out, cudaStream_t s)
+{
+    *out = nullptr;
+    StreamPlan *P = new (std::nothrow) StreamPlan();
+    if (!P) {
+        set_error("host allocation failed");
+        return CSRK_ENOMEM;
+    }
+    P->x_kind = x_kind;
+    const int64_t g = options().stream_ctas.load(), nw = options().stream_warps.load();
+    P->G = (int)(g > 0 ? std::min<int64_t>(g, 4 * (int64_t)ctx().sm_count) : ctx().sm_count);
+    P->NW = (int)std::min<int64_t>(std::max<int64_t>(nw, 1), SL_MAX_WARPS);
+    P->piece = (int)std::min<int64_t>(std::max<int64_t>(options().stream_piece.load(), 8), 4096);
+    P->ring = options().stream_ring_bytes.load() >= 8192 ? 8192 : 4096;
+    P->nst = options().stream_ring_chunks.load() == 2 ? 2 : 4;
+    if (h->val_kind == 8)
+        P->ring = 8192;   // a J group of float64 values is up to 2.7 KB and must fit three chunks
+    P->NW = (int)std::min<int64_t>(P->NW, (int64_t)(ctx().smem_optin / 2) / P->ring);   // rings take at most half
+    int rc;
+    {
+        WsScope scope;
+        if (h->rp_is64)
+            rc = h->val_kind == 4   ? stream_build_typed<int64_t, float>(h, P, s)
+                 : h->val_kind == 8 ? stream_build_typed<int64_t, double>(h, P, s)
+                                    : stream_build_typed<int64_t, NoPayload>(h, P, s);
+        else
+            rc = h->val_kind == 4   ? stream_build_typed<int32_t, float>(h, P, s)
+                 : h->val_kind == 8 ? stream_build_typed<int32_t, double>(h, P, s)
+                                    : stream_build_typed<int32_t, NoPayload>(h, P, s);
+        if (rc != CSRK_OK)
+            (void)cudaStreamSynchronize(s);  // nothing may still read the workspace when the scope rewinds it
+    }
+    if (rc != CSRK_OK) {
+        stream_destroy(P, s);
+        return rc;
+    }
+    *out = P;
+    return CSRK_OK;
+}
+
+// ------------------------------------------------------------------ kernel
+__device__ __forceinline__ uint32_t sl_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sl_bar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sl_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sl_expect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sl_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sl_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sl_u32(bar)) : "memory");
+}
+// `backoff` > 0: sleep that many ns between polls (coarse waits: an x slab; a spinning warp steals issue slots)
+__device__ __forceinline__ void sl_wait(uint64_t *bar, uint32_t parity, unsigned backoff = 0)
+{
+    uint32_t ok = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(sl_u32(bar)), "r"(parity)
+                     : "memory");
+        if (ok)
+            break;
+        if (backoff)
+            __nanosleep(backoff);
+    }
+}
+__device__ __forceinline__ void sl_bulk(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sl_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(sl_u32(bar))
+                 : "memory");
+}
+
+template <typename VT, typename XT> __device__ __forceinline__ double sl_prod(VT v, XT xv)
+{
+    if constexpr (std::is_same<VT, NoVal>::value) {
+        return (double)xv;
+    } else {
+        using PT = typename Prod<VT, XT>::type;   // numba's promotion: f4*f4 -> f4, else f8; the product is
+        if constexpr (std::is_same<PT, float>::value)  // rounded before it is added (no FMA contraction)
+            return (double)__fmul_rn((float)xv, (float)v);
+        else
+            return __dmul_rn((double)xv, (double)v);
+    }
+}
+
+struct SlArgs {
+    const unsigned char *stream;
+    const int64_t *binbase;
+    const uint32_t *binlen;
+    const int32_t *rowmap;
+    int nslab, S, P, NW, slab_bytes, ring, nst;
+    int32_t ncols;
+};
+
+// A warp's view of its ring: bytes [0, avail) of the stream have landed, chunks [0, tail) were requested.
+// Stream offset o lives at ring byte o & mask; the ring starts at a multiple of its size inside the dynamic
+// shared memory, so `base | (o & mask)` is its offset there (one LOP3).
+struct SlRing {
+    const unsigned char *smem;   // start of the dynamic shared memory
+    uint32_t base;               // offset of this warp's ring in it
+    uint64_t *full;              // [nst]
+    const unsigned char *src;
+    uint32_t len, mask, chunk, csh, nst, nsh;
+    uint32_t avail, tail;
+    int lane;
+
+    __device__ __forceinline__ void request(uint32_t i)
+    {
+        const uint32_t st = i & (nst - 1);
+        sl_expect(&full[st], chunk);
+        sl_bulk(const_cast<unsigned char *>(smem) + base + st * chunk, src + (size_t)i * chunk, chunk, &full[st]);
+    }
+    __device__ __forceinline__ void start()
+    {
+        avail = 0;
+        tail = nst;
+        if (lane == 0)
+            for (uint32_t i = 0; i < nst; i++)
+                if (i * chunk < len)
+                    request(i);
+    }
+    // make bytes [.., end) readable
+    __device__ __forceinline__ void ensure(uint32_t end)
+    {
+#pragma unroll 1
+        while (avail < end) {
+            const uint32_t i = avail >> csh;
+            sl_wait(&full[i & (nst - 1)], (i >> nsh) & 1u);
+            avail += chunk;
+        }
+    }
+    // everything below `pos` has been consumed by all lanes (call after __syncwarp): refill the freed chunks
+    __device__ __forceinline__ void release(uint32_t pos)
+    {
+        const uint32_t want = (pos >> csh) + nst;
+        if (tail < want) {
+            if (lane == 0) {
+#pragma unroll 1
+                for (uint32_t i = tail; i < want; i++)
+                    if (i * chunk < len)
+                        request(i);
+            }
+            tail = want;
+        }
+    }
+    template <typename T> __device__ __forceinline__ T at(uint32_t off) const
+    {
+        return *reinterpret_cast<const T *>(smem + (base | (off & mask)));
+    }
+};
+
+// the term of one entry in the type numba computes it in (f4*f4 -> f4, else f8; no value: x itself), rounded
+// before it is added (no FMA contraction)
+template <typename VT, typename XT> struct SlTerm {
+    using type = typename Prod<VT, XT>::type;
+};
+template <typename XT> struct SlTerm<NoVal, XT> {
+    using type = XT;
+};
+template <typename VT, typename XT>
+__device__ __forceinline__ typename SlTerm<VT, XT>::type sl_term(const SlRing &R, uint32_t voff, XT xv)
+{
+    using PT = typename SlTerm<VT, XT>::type;
+    if constexpr (std::is_same<VT, NoVal>::value)
+        return xv;
+    else if constexpr (std::is_same<PT, float>::value)
+        return __fmul_rn((float)xv, (float)R.template at<VT>(voff));
+    else
+        return __dmul_rn((double)xv, (double)R.template at<VT>(voff));
+}
+
+// steps T0..T1-1 of a J group, fully predicated (no branches): the loads of all steps are independent.
+// e[t] = entries before step t; lane l's entry of step t is number e[t] + l of the group.
+template <int T0, int T1, typename VT, typename XT>
+__device__ __forceinline__ void sl_steps(const SlRing &R, const int lk, const uint32_t cl, const uint32_t vl,
+                                         const uint32_t (&e)[SL_TB], const XT *__restrict__ xs, double &sum)
+{
+    constexpr int VB = std::is_same<VT, NoVal>::value ? 0 : (int)sizeof(VT);
+#pragma unroll
+    for (int t = T0; t < T1; t++) {
+        const bool act = t < lk;
+        uint32_t c = R.template at<uint16_t>(cl + 2u * e[t]);
+        c = act ? c : 0u;   // lanes past their run read someone else's bytes: keep the gather inside the slab
+        auto p = sl_term<VT, XT>(R, vl + (uint32_t)VB * e[t], xs[c]);
+        p = act ? p : decltype(p)(0);   // (what such a lane read is arbitrary, NaN included)
+        sum += (double)p;
+    }
+}
+
+template <typename VT, typename XT, bool MULTI>
+__global__ void __launch_bounds__(1024, 1)
+k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ carry)
+{
+    constexpr int VB = std::is_same<VT, NoVal>::value ? 0 : (int)sizeof(VT);
+    extern __shared__ __align__(1024) unsigned char sl_smem[];
+    const size_t xstride = (size_t)a.slab_bytes + 128;                                 // slab + the zero slot
+    unsigned char *xbuf = sl_smem + (size_t)a.NW * a.ring;                             // rings first: [NW][ring]; then [2][xstride]
+    double *acc = reinterpret_cast<double *>(xbuf + 2 * xstride);                      // [NW][P+1]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(acc + (size_t)a.NW * (a.P + 1));     // full[2], empty[2], ring[NW][nst]
+    uint64_t *full = bars, *empty = bars + 2, *rbar = bars + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        sl_bar_init(&full[0], 1);
+        sl_bar_init(&full[1], 1);
+        sl_bar_init(&empty[0], a.NW);
+        sl_bar_init(&empty[1], a.NW);
+        for (int i = 0; i < a.NW * a.nst; i++)
+            sl_bar_init(&rbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid < 2)
+        reinterpret_cast<XT *>(xbuf + tid * xstride)[a.S] = XT(0);   // what the inert entries multiply
+    __syncthreads();   // the only CTA-wide barrier
+    // CTA g walks the slabs starting at slab g*nslab/G and wraps around, so that at any moment the CTAs pull
+    // different parts of x out of L2
+    const int slab0 = (int)(((int64_t)blockIdx.x * a.nslab) / gridDim.x);
+
+    if (warp == a.NW) {
+        // ---------------- producer: the k-th slab of this CTA's walk into buffer k & 1
+        if (lane == 0) {
+            for (int k = 0; k < a.nslab; k++) {
+                const int st = k & 1;
+                if (k >= 2)
+                    sl_wait(&empty[st], (uint32_t)(((k >> 1) - 1) & 1), 200);
+                int s = k + slab0;
+                if (s >= a.nslab)
+                    s -= a.nslab;
+                const int64_t c0 = (int64_t)s * a.S;
+                const int n = (int)min((int64_t)a.S, (int64_t)a.ncols - c0);
+                const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(XT), b16 = bytes & ~15u;
+                XT *dst = reinterpret_cast<XT *>(xbuf + st * xstride);
+                for (int i = (int)(b16 / sizeof(XT)); i < n; i++)   // < 16 bytes that a bulk copy cannot move
+                    dst[i] = x[c0 + i];
+                if (b16) {
+                    sl_expect(&full[st], b16);
+                    for (uint32_t o = 0; o < b16; o += 16384)
+                        sl_bulk(reinterpret_cast<unsigned char *>(dst) + o, reinterpret_cast<const unsigned char *>(x + c0) + o,
+                                min(16384u, b16 - o), &full[st]);
+                } else {
+                    sl_arrive(&full[st]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: warp `warp` owns bin (blockIdx.x, warp)
+    const int64_t bin = (int64_t)blockIdx.x * a.NW + warp;
+    double *acc_w = acc + (size_t)warp * (a.P + 1);
+    SlRing R;
+    R.smem = sl_smem;
+    R.base = (uint32_t)warp * (uint32_t)a.ring;
+    R.nst = (uint32_t)a.nst;
+    R.nsh = a.nst == 2 ? 1u : 2u;
+    R.full = rbar + warp * a.nst;
+    R.src = a.stream + a.binbase[bin];
+    R.len = a.binlen[bin];
+    R.mask = (uint32_t)a.ring - 1u;
+    R.chunk = (uint32_t)a.ring / R.nst;
+    R.csh = 31 - __clz((int)R.chunk);
+    R.lane = lane;
+    R.start();
+    for (int i = lane; i <= a.P; i += 32)
+        acc_w[i] = 0.0;
+    __syncwarp();
+    uint32_t pos = 0;
+    for (int k = 0; k < a.nslab; k++) {
+        R.ensure(pos + 16);
+        const uint2 hdr = R.at<uint2>(pos);   // J groups, 32-entry L blocks
+        pos += 16;
+        const int st = k & 1;
+        sl_wait(&full[st], (uint32_t)((k >> 1) & 1), 100);
+        const XT *xs = reinterpret_cast<const XT *>(xbuf + st * xstride);
+        // J groups: lane l sums run l over the group's steps
+#pragma unroll 1
+        for (uint32_t j = 0; j < hdr.x; j++) {
+            R.ensure(pos + SL_HDR);
+            const uint32_t m = R.at<uint32_t>(pos + 4u * lane);   // row << 16 | steps << 8 | my entries
+            const uint4 o = R.at<uint4>(pos + 128);
+            const uint32_t e[SL_TB] = {0u,           o.x & 0xffffu, o.x >> 16,     o.y & 0xffffu,
+                                       o.y >> 16,    o.z & 0xffffu, o.z >> 16,     o.w & 0xffffu};
+            const uint32_t n = o.w >> 16;
+            const uint32_t cl = pos + SL_HDR + 2u * lane, vl = pos + SL_HDR + sl_pad16(2u * n) + (uint32_t)VB * lane;
+            const uint32_t end = pos + SL_HDR + sl_pad16(2u * n) + sl_pad16((uint32_t)VB * n);
+            R.ensure(end);
+            const int lk = (int)(m & 0xffu);
+            double sum = 0.0;
+            sl_steps<0, 6, VT, XT>(R, lk, cl, vl, e, xs, sum);
+            if (((m >> 8) & 0xffu) > 6)
+                sl_steps<6, SL_TB, VT, XT>(R, lk, cl, vl, e, xs, sum);
+            if (lk)
+                acc_w[m >> 16] += sum;
+            __syncwarp();
+            pos = end;
+            R.release(pos);
+        }
+        // L blocks: one entry per lane, all rows of a cell's L blocks distinct; up to four blocks at a time
+#pragma unroll 1
+        for (uint32_t j = 0; j < hdr.y; j += 4) {
+            const uint32_t nb = min(hdr.y - j, 4u);
+            const uint32_t end = pos + nb * (128 + 32 * VB);
+            R.ensure(end);
+            uint32_t w[4];
+            typename SlTerm<VT, XT>::type p[4];
+            double old[4];
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                // (blocks past nb: the ring offset is masked, so the read is harmless; its result is unused)
+                const uint32_t bo = pos + i * (128 + 32 * VB);
+                w[i] = R.at<uint32_t>(bo + 4u * lane);
+                w[i] = i < nb ? w[i] : ((uint32_t)a.P << 16 | (uint32_t)a.S);
+                p[i] = sl_term<VT, XT>(R, bo + 128 + (uint32_t)VB * lane, xs[w[i] & 0xffffu]);
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++)
+                old[i] = acc_w[w[i] >> 16];
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++)
+                if (i < nb)
+                    acc_w[w[i] >> 16] = old[i] + (double)p[i];
+            __syncwarp();
+            pos = end;
+            R.release(pos);
+        }
+        if (lane == 0)
+            sl_arrive(&empty[st]);   // this warp is done with the slab
+    }
+    // ---------------- results: rows straight to y, pieces of split rows to their carry slots
+    const int32_t *rm = a.rowmap + bin * a.P;
+    for (int i = lane; i < a.P; i += 32) {
+        const int32_t r = rm[i];
+        if (r >= 0)
+            store_y<MULTI>(y, r, acc_w[i], true);
+        else if (r <= -2)
+            carry[-(r + 2)] = acc_w[i];
+    }
+}
+
+// one thread per split row: add its pieces in piece order (deterministic)
+template <bool MULTI>
+__global__ void k_slab_fixup(const int32_t *__restrict__ split, int n_split, const double *__restrict__ carry, YOut y)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_split)
+        return;
+    const int32_t row = split[3 * k], q0 = split[3 * k + 1], nq = split[3 * k + 2];
+    double tot = 0.0;
+    for (int j = 0; j < nq; j++)
+        tot += carry[q0 + j];
+    store_y<MULTI>(y, row, tot, true);
+}
+
+template <typename VT, typename XT, bool MULTI>
+static int slab_launch(StreamPlan *P, const SlArgs &a, const void *d_x, const YOut &y, double *carry, cudaStream_t s)
+{
+    auto k = k_spmv_slab<VT, XT, MULTI>;
+    static size_t optin = 0;   // per instantiation
+    if (optin < P->smem_bytes) {
+        CSRK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx().smem_optin));
+        optin = ctx().smem_optin;
+    }
+    CSRK_LAUNCH(k, (unsigned)P->G, (unsigned)(P->NW + 1) * 32, P->smem_bytes, s, a, (const XT *)d_x, y, carry);
+    if (P->n_split)
+        CSRK_LAUNCH((k_slab_fixup<MULTI>), (unsigned)div_up(P->n_split, 128), 128, 0, s, P->split, P->n_split, carry, y);
+    return CSRK_OK;
+}
+
+template <typename VT, typename XT>
+static int slab_launch_m(StreamPlan *P, const SlArgs &a, const void *d_x, const YOut &y, double *carry, cudaStream_t s)
+{
+    if (y.n > 1)
+        return slab_launch<VT, XT, true>(P, a, d_x, y, carry, s);
+    return slab_launch<VT, XT, false>(P, a, d_x, y, carry, s);
+}
+
+template <typename VT>
+static int slab_launch_x(StreamPlan *P, const SlArgs &a, const void *d_x, const YOut &y, double *carry, cudaStream_t s)
+{
+    if (P->x_kind == 4)
+        return slab_launch_m<VT, float>(P, a, d_x, y, carry, s);
+    return slab_launch_m<VT, double>(P, a, d_x, y, carry, s);
+}
+
+int stream_run(csrk_matrix *h, StreamPlan *P, const void *d_x, const YOut &y, cudaStream_t s)
+{
+    SlArgs a;
+    a.stream = P->stream;
+    a.binbase = P->binbase;
+    a.binlen = P->binlen;
+    a.rowmap = P->rowmap;
+    a.nslab = P->nslab;
+    a.S = P->S;
+    a.P = P->P;
+    a.NW = P->NW;
+    a.slab_bytes = P->slab_bytes;
+    a.ring = P->ring;
+    a.nst = P->nst;
+    a.ncols = h->ncols;
+    // carry slots of the split rows: per call (concurrent calls on one handle must not share them)
+    DevBuf carry;
+    if (P->n_split)
+        CSRK_TRY(carry.alloc(sizeof(double) * (size_t)P->Q, s));
+    switch (h->val_kind) {
+    case 4: return slab_launch_x<float>(P, a, d_x, y, carry.as<double>(), s);
+    case 8: return slab_launch_x<double>(P, a, d_x, y, carry.as<double>(), s);
+    default: return slab_launch_x<NoVal>(P, a, d_x, y, carry.as<double>(), s);
+    }
+}
+
+void stream_info(const StreamPlan *P, int64_t *out /*[11]*/)
+{
+    out[0] = P->G, out[1] = P->NW, out[2] = P->nslab, out[3] = P->S, out[4] = P->P, out[5] = P->Q, out[6] = P->n_split,
+    out[7] = (int64_t)P->smem_bytes, out[8] = P->stream_bytes, out[9] = P->piece, out[10] = P->ring;
+}
+
+}  // namespace csrk

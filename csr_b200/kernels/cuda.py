@@ -313,9 +313,10 @@ def from_device_arrays(nrows, ncols, nnz, rowptrs_ptr, rp_is64, colinds_ptr, val
 def spmv_plan_info(h: cuda_h, x_itemsize: int = 4) -> dict:
     """Which SpMV kernel serves ``h`` for x of the given item size (the plan is built by the first
     ``mult_vec`` that selects it): ``{'kernel': 'stream' | 'tile', ...plan shape}``."""
-    info = (C.c_int64 * 9)()
+    info = (C.c_int64 * 12)()
     N.check(N.lib().csrk_spmv_plan_info(_live(h), int(x_itemsize), info), "spmv_plan_info")
-    names = ("ctas", "warps", "slabs", "slab_cols", "rows_per_warp", "pseudo_rows", "split_rows", "smem_bytes")
+    names = ("ctas", "warps", "slabs", "slab_cols", "rows_per_warp", "pseudo_rows", "split_rows", "smem_bytes",
+             "stream_bytes", "piece", "ring_bytes")
     out = {"kernel": "stream" if info[0] else "tile"}
     if info[0]:
         out.update({n: int(info[i + 1]) for i, n in enumerate(names)})

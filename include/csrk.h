@@ -64,7 +64,9 @@ int csrk_synchronize(void);
 /* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 slab-stream kernel (x staged in shared memory);
  * "stream_min_nnz" smallest nnz for which auto mode builds a stream plan;
  * "stream_slab_bytes" > 0 caps the x slab size, "stream_ctas" > 0 sets the number of CTAs (row groups),
- *               "stream_warps" 1..31 the consumer warps per CTA of the slab-stream kernel (tests, tuning);
+ *               "stream_warps" 1..31 the consumer warps per CTA of the slab kernel, "stream_piece" 8..4096 the
+ *               longest pseudo-row (longer rows are cut), "stream_ring_bytes" 4096 | 8192 the per-warp prefetch
+ *               ring (tests, tuning);
  * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
  * "spmv_zero_copy_y" 1 | 0: csrk_spmv stores finished rows straight into y when y is pinned host memory;
  * "fix_threads" 512 | 768 | 1024 threads per CTA of that kernel (default 1024);
@@ -113,10 +115,11 @@ int csrk_subset_rows(csrk_h h, int32_t begin, int32_t end, csrk_h *out);
  * row directly into it over PCIe, overlapping the device-to-host transfer with the compute. */
 int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y);
 /* Which SpMV kernel serves this handle for x of x_kind, and the shape of its plan:
- * info[0] = 1 when a slab-stream plan exists (built by the first mult_vec that selected it), else 0 (CSR
- * tile kernel); info[1..8] = CTAs, consumer warps per CTA, x slabs, columns per slab, pseudo-rows per warp,
- * pseudo-rows, split rows, shared-memory bytes per CTA. */
-int csrk_spmv_plan_info(csrk_h h, int x_kind, int64_t info[9]);
+ * info[0] = 1 when a slab plan exists (built by the first mult_vec that selected it), else 0 (CSR tile
+ * kernel); info[1..11] = CTAs, consumer warps per CTA, x slabs, columns per slab, pseudo-rows per warp,
+ * pseudo-rows, split rows, shared-memory bytes per CTA, bytes of the re-laid-out entry stream, longest
+ * pseudo-row, prefetch ring bytes per warp. */
+int csrk_spmv_plan_info(csrk_h h, int x_kind, int64_t info[12]);
 /* Device pointers; y has nrows doubles. */
 int csrk_spmv_dev(csrk_h h, const void *d_x, int x_kind, double *d_y, void *stream);
 /* Fused SpMV + gather for the row-partitioned multi-GPU SpMV: every finished row is stored to
