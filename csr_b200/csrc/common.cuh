@@ -136,6 +136,7 @@ struct Options {
     std::atomic<int64_t> stream_piece{512};             // longest pseudo-row: longer rows are cut into interleaved pieces
     std::atomic<int64_t> stream_ring_bytes{4096};       // per-warp prefetch ring of the entry stream (4096 | 8192)
     std::atomic<int64_t> stream_ring_chunks{4};         // chunks (bulk copies) per ring: 2 | 4
+    std::atomic<int64_t> stream_xbufs{2};               // x slabs resident per CTA: 2 | 3
     std::atomic<int64_t> radix_bits{0};                 // digit width of the stable sort: 0 = pick (9 when it saves a pass), 8, 9
     std::atomic<int64_t> spmv_zero_copy_y{1};           // csrk_spmv: store rows straight into pinned host y
     std::atomic<int64_t> fix_threads{1024};             // threads per CTA of the fixed-point SpGEMM kernel (512 | 768 | 1024)

@@ -390,6 +390,9 @@ int csrk_set_option(const char *name, int64_t value)
     } else if (!strcmp(name, "stream_ring_chunks")) {
         CSRK_ARG(value == 2 || value == 4, "stream_ring_chunks must be 2 or 4");
         options().stream_ring_chunks = value;
+    } else if (!strcmp(name, "stream_xbufs")) {
+        CSRK_ARG(value == 2 || value == 3, "stream_xbufs must be 2 or 3");
+        options().stream_xbufs = value;
     } else if (!strcmp(name, "radix_bits")) {
         CSRK_ARG(value == 0 || value == 8 || value == 9, "radix_bits must be 0, 8 or 9");
         options().radix_bits = value;

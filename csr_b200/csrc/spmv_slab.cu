@@ -42,12 +42,12 @@
 namespace csrk {
 
 constexpr int SL_TB = 8;                   // steps per J group
-constexpr int SL_HDR = 144;                // J group header: 32 x (row << 16 | len), n, T, 0, 0
+constexpr int SL_HDR = 160;                // J group header: 32 x (row << 16 | steps << 8 | len), 16 x u16 byte offsets
 constexpr int SL_NST_MAX = 4;              // chunks per ring: 2 or 4
 constexpr int SL_MAX_WARPS = 31;           // consumer warps (+1 producer warp = 1024 threads)
 
 struct StreamPlan {
-    int G = 0, NW = 0, nslab = 0, S = 0, P = 0, x_kind = 0, piece = 0, ring = 0, nst = 4;
+    int G = 0, NW = 0, nslab = 0, S = 0, P = 0, x_kind = 0, piece = 0, ring = 0, nst = 4, nxb = 2;
     int slab_bytes = 0;
     size_t smem_bytes = 0;
     int64_t Q = 0, stream_bytes = 0;
@@ -340,7 +340,8 @@ k_sl_fill(int64_t NI, const int64_t *__restrict__ itembase, int64_t ncells, cons
         const int Tk = min(T - t0, SL_TB);
         const int n = warp_sum(lk);
         reinterpret_cast<uint32_t *>(o)[lane] = row << 16 | (uint32_t)Tk << 8 | (uint32_t)lk;
-        uint16_t *offs = reinterpret_cast<uint16_t *>(o + 128);   // entries before step 1..7, then n
+        // byte offsets of steps 1..7 inside the column and value sections; slot 7 of the first eight = n
+        uint16_t *offs = reinterpret_cast<uint16_t *>(o + 128);
         uint16_t *cols = reinterpret_cast<uint16_t *>(o + SL_HDR);
         unsigned char *vals = o + SL_HDR + sl_pad16(2u * n);
         int off = 0;
@@ -354,8 +355,10 @@ k_sl_fill(int64_t NI, const int64_t *__restrict__ itembase, int64_t ncells, cons
                     reinterpret_cast<VT *>(vals)[off + lane] = svals[src];
             }
             off += __popc(bal);
-            if (lane == 0)
-                offs[t] = (uint16_t)off;   // offs[7] = n
+            if (lane == 0) {
+                offs[t] = (uint16_t)(t < SL_TB - 1 ? 2 * off : off);   // offs[7] = n
+                offs[8 + t] = (uint16_t)(t < SL_TB - 1 ? VB * off : 0);
+            }
         }
         o += SL_HDR + sl_pad16(2u * n) + sl_pad16((uint32_t)VB * n);
     }
@@ -401,15 +404,16 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     CSRK_CUDA(cudaStreamSynchronize(s));
     P->Q = Q;
     P->P = (int)std::max<int64_t>(div_up(Q, B), 1);
-    // shared memory: NW rings + NW*(P+1) float64 accumulators + mbarriers + two x slabs
+    // shared memory: mbarriers + alignment of the rings (up to one ring) + NW rings + NW*(P+1) float64
+    // accumulators + nxb x slabs
     const size_t acc_bytes = (size_t)P->NW * (P->P + 1) * 8;
     const size_t ring_bytes = (size_t)P->NW * P->ring;
-    const size_t bar_bytes = (size_t)(4 + P->NW * SL_NST_MAX) * 8;
+    const size_t bar_bytes = (size_t)(2 * 3 + P->NW * SL_NST_MAX) * 8 + 16 + (size_t)P->ring;
     const size_t smem_max = ctx().smem_optin;
-    if (P->P > 65534 || Q >= ((int64_t)1 << 31) || acc_bytes + ring_bytes + bar_bytes + 2 * 4096 > smem_max)
+    if (P->P > 65534 || Q >= ((int64_t)1 << 31) || acc_bytes + ring_bytes + bar_bytes + (size_t)P->nxb * 4096 > smem_max)
         return CSRK_EOVERFLOW;  // too many rows for shared-memory accumulators: stay on the tile kernel
     // a buffer is one slab + 128 bytes (the always-zero slot the inert entries point at)
-    int64_t slab = (int64_t)((smem_max - acc_bytes - ring_bytes - bar_bytes) / 2 - 128) & ~(int64_t)127;
+    int64_t slab = (int64_t)((smem_max - acc_bytes - ring_bytes - bar_bytes) / P->nxb - 128) & ~(int64_t)127;
     slab = std::min<int64_t>(slab, (int64_t)65408 * P->x_kind);   // columns inside a slab (and the zero slot) fit 16 bits
     slab = std::min<int64_t>(slab, (((int64_t)h->ncols * P->x_kind) + 127) & ~(int64_t)127);
     const int64_t cap = options().stream_slab_bytes.load();
@@ -419,7 +423,7 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     P->slab_bytes = (int)slab;
     P->S = (int)(slab / P->x_kind);
     P->nslab = (int)std::max<int64_t>(div_up((int64_t)h->ncols, P->S), 1);
-    P->smem_bytes = ring_bytes + 2 * ((size_t)slab + 128) + acc_bytes + bar_bytes;
+    P->smem_bytes = ring_bytes + (size_t)P->nxb * ((size_t)slab + 128) + acc_bytes + bar_bytes;
     const int64_t ncells = (int64_t)B * P->nslab;
     const int LB = sl_bits((int64_t)P->piece + 2);   // run lengths 1..piece (duplicate columns may exceed S)
     if (ncells >= ((int64_t)1 << (30 - LB)))
@@ -544,6 +548,7 @@ int stream_build(csrk_matrix *h, int x_kind, StreamPlan **out, cudaStream_t s)
     P->piece = (int)std::min<int64_t>(std::max<int64_t>(options().stream_piece.load(), 8), 4096);
     P->ring = options().stream_ring_bytes.load() >= 8192 ? 8192 : 4096;
     P->nst = options().stream_ring_chunks.load() == 2 ? 2 : 4;
+    P->nxb = options().stream_xbufs.load() == 3 ? 3 : 2;
     if (h->val_kind == 8)
         P->ring = 8192;   // a J group of float64 values is up to 2.7 KB and must fit three chunks
     P->NW = (int)std::min<int64_t>(P->NW, (int64_t)(ctx().smem_optin / 2) / P->ring);   // rings take at most half
@@ -624,17 +629,60 @@ struct SlArgs {
     const int64_t *binbase;
     const uint32_t *binlen;
     const int32_t *rowmap;
-    int nslab, S, P, NW, slab_bytes, ring, nst;
+    int nslab, S, P, NW, slab_bytes, ring, nst, nxb;
     int32_t ncols;
 };
 
+// shared-memory accesses by 32-bit shared address (the ring offset arithmetic below is done on addresses)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+template <typename T> __device__ __forceinline__ T lds_val(uint32_t a);
+template <> __device__ __forceinline__ float lds_val<float>(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+template <> __device__ __forceinline__ double lds_val<double>(uint32_t a) { return lds_f64(a); }
+
 // A warp's view of its ring: bytes [0, avail) of the stream have landed, chunks [0, tail) were requested.
-// Stream offset o lives at ring byte o & mask; the ring starts at a multiple of its size inside the dynamic
-// shared memory, so `base | (o & mask)` is its offset there (one LOP3).
+// The ring's shared-memory ADDRESS is a multiple of its size, so stream offset o lives at address
+// base | (o & mask): one LOP3.
 struct SlRing {
-    const unsigned char *smem;   // start of the dynamic shared memory
-    uint32_t base;               // offset of this warp's ring in it
-    uint64_t *full;              // [nst]
+    uint32_t base;               // shared address of this warp's ring
+    uint32_t full;               // shared address of its nst mbarriers
     const unsigned char *src;
     uint32_t len, mask, chunk, csh, nst, nsh;
     uint32_t avail, tail;
@@ -643,8 +691,11 @@ struct SlRing {
     __device__ __forceinline__ void request(uint32_t i)
     {
         const uint32_t st = i & (nst - 1);
-        sl_expect(&full[st], chunk);
-        sl_bulk(const_cast<unsigned char *>(smem) + base + st * chunk, src + (size_t)i * chunk, chunk, &full[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full + 8 * st), "r"(chunk) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         base + st * chunk),
+                     "l"(src + (size_t)i * chunk), "r"(chunk), "r"(full + 8 * st)
+                     : "memory");
     }
     __device__ __forceinline__ void start()
     {
@@ -661,7 +712,14 @@ struct SlRing {
 #pragma unroll 1
         while (avail < end) {
             const uint32_t i = avail >> csh;
-            sl_wait(&full[i & (nst - 1)], (i >> nsh) & 1u);
+            const uint32_t bar = full + 8 * (i & (nst - 1)), parity = (i >> nsh) & 1u;
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(bar), "r"(parity)
+                    : "memory");
             avail += chunk;
         }
     }
@@ -679,10 +737,7 @@ struct SlRing {
             tail = want;
         }
     }
-    template <typename T> __device__ __forceinline__ T at(uint32_t off) const
-    {
-        return *reinterpret_cast<const T *>(smem + (base | (off & mask)));
-    }
+    __device__ __forceinline__ uint32_t addr(uint32_t off) const { return base | (off & mask); }
 };
 
 // the term of one entry in the type numba computes it in (f4*f4 -> f4, else f8; no value: x itself), rounded
@@ -694,32 +749,39 @@ template <typename XT> struct SlTerm<NoVal, XT> {
     using type = XT;
 };
 template <typename VT, typename XT>
-__device__ __forceinline__ typename SlTerm<VT, XT>::type sl_term(const SlRing &R, uint32_t voff, XT xv)
+__device__ __forceinline__ typename SlTerm<VT, XT>::type sl_term(uint32_t vaddr, XT xv)
 {
     using PT = typename SlTerm<VT, XT>::type;
     if constexpr (std::is_same<VT, NoVal>::value)
         return xv;
     else if constexpr (std::is_same<PT, float>::value)
-        return __fmul_rn((float)xv, (float)R.template at<VT>(voff));
+        return __fmul_rn((float)xv, (float)lds_val<VT>(vaddr));
     else
-        return __dmul_rn((double)xv, (double)R.template at<VT>(voff));
+        return __dmul_rn((double)xv, (double)lds_val<VT>(vaddr));
+}
+// v if keep else +0, chosen on the bits (what a masked lane computed is arbitrary, NaN included)
+__device__ __forceinline__ float sl_keep(float v, bool keep) { return __uint_as_float(keep ? __float_as_uint(v) : 0u); }
+__device__ __forceinline__ double sl_keep(double v, bool keep)
+{
+    return __longlong_as_double(keep ? __double_as_longlong(v) : 0ll);
 }
 
 // steps T0..T1-1 of a J group, fully predicated (no branches): the loads of all steps are independent.
-// e[t] = entries before step t; lane l's entry of step t is number e[t] + l of the group.
+// co[t] / vo[t] = byte offset of step t inside the column / value section; lane l's entry is the l-th there.
+// A lane past the end of its run reads the ZERO PAD instead (column S = the always-zero x slot, value 0):
+// its term is exactly 0 whatever the other lanes' entries hold.
 template <int T0, int T1, typename VT, typename XT>
 __device__ __forceinline__ void sl_steps(const SlRing &R, const int lk, const uint32_t cl, const uint32_t vl,
-                                         const uint32_t (&e)[SL_TB], const XT *__restrict__ xs, double &sum)
+                                         const uint32_t (&co)[SL_TB], const uint32_t (&vo)[SL_TB], const uint32_t xs,
+                                         const uint32_t zpad, double &sum)
 {
-    constexpr int VB = std::is_same<VT, NoVal>::value ? 0 : (int)sizeof(VT);
 #pragma unroll
     for (int t = T0; t < T1; t++) {
         const bool act = t < lk;
-        uint32_t c = R.template at<uint16_t>(cl + 2u * e[t]);
-        c = act ? c : 0u;   // lanes past their run read someone else's bytes: keep the gather inside the slab
-        auto p = sl_term<VT, XT>(R, vl + (uint32_t)VB * e[t], xs[c]);
-        p = act ? p : decltype(p)(0);   // (what such a lane read is arbitrary, NaN included)
-        sum += (double)p;
+        const uint32_t ca = act ? R.addr(cl + co[t]) : zpad;
+        const uint32_t va = act ? R.addr(vl + vo[t]) : zpad + 8u;
+        const XT xv = lds_val<XT>(xs + lds_u16(ca) * (uint32_t)sizeof(XT));
+        sum += (double)sl_term<VT, XT>(va, xv);
     }
 }
 
@@ -727,38 +789,46 @@ template <typename VT, typename XT, bool MULTI>
 __global__ void __launch_bounds__(1024, 1)
 k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ carry)
 {
-    constexpr int VB = std::is_same<VT, NoVal>::value ? 0 : (int)sizeof(VT);
+    constexpr uint32_t VB = std::is_same<VT, NoVal>::value ? 0u : (uint32_t)sizeof(VT);
     extern __shared__ __align__(1024) unsigned char sl_smem[];
-    const size_t xstride = (size_t)a.slab_bytes + 128;                                 // slab + the zero slot
-    unsigned char *xbuf = sl_smem + (size_t)a.NW * a.ring;                             // rings first: [NW][ring]; then [2][xstride]
-    double *acc = reinterpret_cast<double *>(xbuf + 2 * xstride);                      // [NW][P+1]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(acc + (size_t)a.NW * (a.P + 1));     // full[2], empty[2], ring[NW][nst]
-    uint64_t *full = bars, *empty = bars + 2, *rbar = bars + 4;
+    // layout: mbarriers | (pad to a multiple of the ring size in the shared ADDRESS space) rings[NW] | x[nxb] | acc[NW][P+1]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sl_smem);   // full[nxb], empty[nxb], ring[NW][nst], zero pad
+    uint64_t *full = bars, *empty = bars + a.nxb, *rbar = bars + 2 * a.nxb;
+    const uint32_t smem0 = sl_u32(sl_smem);
+    const uint32_t zpad = smem0 + (uint32_t)(2 * a.nxb + a.NW * a.nst) * 8u;   // 16 bytes: u16 column S, 8 zero bytes
+    const uint32_t ring0 = (zpad + 16u + (uint32_t)a.ring - 1u) & ~((uint32_t)a.ring - 1u);
+    const uint32_t xstride = (uint32_t)a.slab_bytes + 128u;                            // slab + the zero slot
+    const uint32_t xbuf0 = ring0 + (uint32_t)a.NW * (uint32_t)a.ring;
+    unsigned char *xbuf = sl_smem + (xbuf0 - smem0);
+    const uint32_t acc0 = xbuf0 + (uint32_t)a.nxb * xstride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        sl_bar_init(&full[0], 1);
-        sl_bar_init(&full[1], 1);
-        sl_bar_init(&empty[0], a.NW);
-        sl_bar_init(&empty[1], a.NW);
+        for (int i = 0; i < a.nxb; i++) {
+            sl_bar_init(&full[i], 1);
+            sl_bar_init(&empty[i], a.NW);
+        }
         for (int i = 0; i < a.NW * a.nst; i++)
             sl_bar_init(&rbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (tid < 2)
+    if (tid < a.nxb)
         reinterpret_cast<XT *>(xbuf + tid * xstride)[a.S] = XT(0);   // what the inert entries multiply
+    if (tid == 32)
+        *reinterpret_cast<uint4 *>(sl_smem + (zpad - smem0)) = make_uint4((uint32_t)a.S, 0u, 0u, 0u);
     __syncthreads();   // the only CTA-wide barrier
     // CTA g walks the slabs starting at slab g*nslab/G and wraps around, so that at any moment the CTAs pull
     // different parts of x out of L2
     const int slab0 = (int)(((int64_t)blockIdx.x * a.nslab) / gridDim.x);
 
     if (warp == a.NW) {
-        // ---------------- producer: the k-th slab of this CTA's walk into buffer k & 1
+        // ---------------- producer: the k-th slab of this CTA's walk into buffer k % nxb
         if (lane == 0) {
+            int st = 0;
+            uint32_t lap = 0;
             for (int k = 0; k < a.nslab; k++) {
-                const int st = k & 1;
-                if (k >= 2)
-                    sl_wait(&empty[st], (uint32_t)(((k >> 1) - 1) & 1), 200);
+                if (lap)
+                    sl_wait(&empty[st], (lap - 1) & 1u, 1000);
                 int s = k + slab0;
                 if (s >= a.nslab)
                     s -= a.nslab;
@@ -776,6 +846,10 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
                 } else {
                     sl_arrive(&full[st]);
                 }
+                if (++st == a.nxb) {
+                    st = 0;
+                    lap++;
+                }
             }
         }
         return;
@@ -783,13 +857,12 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
 
     // ---------------- consumers: warp `warp` owns bin (blockIdx.x, warp)
     const int64_t bin = (int64_t)blockIdx.x * a.NW + warp;
-    double *acc_w = acc + (size_t)warp * (a.P + 1);
+    const uint32_t acc_w = acc0 + (uint32_t)warp * (uint32_t)(a.P + 1) * 8u;
     SlRing R;
-    R.smem = sl_smem;
-    R.base = (uint32_t)warp * (uint32_t)a.ring;
+    R.base = ring0 + (uint32_t)warp * (uint32_t)a.ring;
     R.nst = (uint32_t)a.nst;
     R.nsh = a.nst == 2 ? 1u : 2u;
-    R.full = rbar + warp * a.nst;
+    R.full = sl_u32(rbar + warp * a.nst);
     R.src = a.stream + a.binbase[bin];
     R.len = a.binlen[bin];
     R.mask = (uint32_t)a.ring - 1u;
@@ -798,35 +871,42 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
     R.lane = lane;
     R.start();
     for (int i = lane; i <= a.P; i += 32)
-        acc_w[i] = 0.0;
+        sts_f64(acc_w + 8u * i, 0.0);
     __syncwarp();
     uint32_t pos = 0;
+    int st = 0;
+    uint32_t lap = 0;
+    const uint32_t inert = (uint32_t)a.P << 16 | (uint32_t)a.S;
     for (int k = 0; k < a.nslab; k++) {
         R.ensure(pos + 16);
-        const uint2 hdr = R.at<uint2>(pos);   // J groups, 32-entry L blocks
+        const uint2 hdr = lds_u32x2(R.addr(pos));   // J groups, 32-entry L blocks
         pos += 16;
-        const int st = k & 1;
-        sl_wait(&full[st], (uint32_t)((k >> 1) & 1), 100);
-        const XT *xs = reinterpret_cast<const XT *>(xbuf + st * xstride);
+        sl_wait(&full[st], lap & 1u, 250);
+        const uint32_t xs = xbuf0 + (uint32_t)st * xstride;
         // J groups: lane l sums run l over the group's steps
 #pragma unroll 1
         for (uint32_t j = 0; j < hdr.x; j++) {
             R.ensure(pos + SL_HDR);
-            const uint32_t m = R.at<uint32_t>(pos + 4u * lane);   // row << 16 | steps << 8 | my entries
-            const uint4 o = R.at<uint4>(pos + 128);
-            const uint32_t e[SL_TB] = {0u,           o.x & 0xffffu, o.x >> 16,     o.y & 0xffffu,
-                                       o.y >> 16,    o.z & 0xffffu, o.z >> 16,     o.w & 0xffffu};
-            const uint32_t n = o.w >> 16;
-            const uint32_t cl = pos + SL_HDR + 2u * lane, vl = pos + SL_HDR + sl_pad16(2u * n) + (uint32_t)VB * lane;
-            const uint32_t end = pos + SL_HDR + sl_pad16(2u * n) + sl_pad16((uint32_t)VB * n);
+            const uint32_t m = lds_u32(R.addr(pos + 4u * lane));   // row << 16 | steps << 8 | my entries
+            const uint4 oc = lds_u32x4(R.addr(pos + 128)), ov = lds_u32x4(R.addr(pos + 144));
+            const uint32_t co[SL_TB] = {0u,         oc.x & 0xffffu, oc.x >> 16,     oc.y & 0xffffu,
+                                        oc.y >> 16, oc.z & 0xffffu, oc.z >> 16,     oc.w & 0xffffu};
+            const uint32_t vo[SL_TB] = {0u,         ov.x & 0xffffu, ov.x >> 16,     ov.y & 0xffffu,
+                                        ov.y >> 16, ov.z & 0xffffu, ov.z >> 16,     ov.w & 0xffffu};
+            const uint32_t n = oc.w >> 16;
+            const uint32_t vsec = pos + SL_HDR + sl_pad16(2u * n);
+            const uint32_t cl = pos + SL_HDR + 2u * lane, vl = vsec + VB * lane;
+            const uint32_t end = vsec + sl_pad16(VB * n);
             R.ensure(end);
             const int lk = (int)(m & 0xffu);
             double sum = 0.0;
-            sl_steps<0, 6, VT, XT>(R, lk, cl, vl, e, xs, sum);
+            sl_steps<0, 6, VT, XT>(R, lk, cl, vl, co, vo, xs, zpad, sum);
             if (((m >> 8) & 0xffu) > 6)
-                sl_steps<6, SL_TB, VT, XT>(R, lk, cl, vl, e, xs, sum);
-            if (lk)
-                acc_w[m >> 16] += sum;
+                sl_steps<6, SL_TB, VT, XT>(R, lk, cl, vl, co, vo, xs, zpad, sum);
+            if (lk) {
+                const uint32_t aa = acc_w + 8u * (m >> 16);
+                sts_f64(aa, lds_f64(aa) + sum);
+            }
             __syncwarp();
             pos = end;
             R.release(pos);
@@ -844,47 +924,54 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
             for (uint32_t i = 0; i < 4; i++) {
                 // (blocks past nb: the ring offset is masked, so the read is harmless; its result is unused)
                 const uint32_t bo = pos + i * (128 + 32 * VB);
-                w[i] = R.at<uint32_t>(bo + 4u * lane);
-                w[i] = i < nb ? w[i] : ((uint32_t)a.P << 16 | (uint32_t)a.S);
-                p[i] = sl_term<VT, XT>(R, bo + 128 + (uint32_t)VB * lane, xs[w[i] & 0xffffu]);
+                w[i] = lds_u32(R.addr(bo + 4u * lane));
+                w[i] = i < nb ? w[i] : inert;
+                p[i] = sl_term<VT, XT>(R.addr(bo + 128 + VB * lane), lds_val<XT>(xs + (w[i] & 0xffffu) * (uint32_t)sizeof(XT)));
             }
 #pragma unroll
             for (uint32_t i = 0; i < 4; i++)
-                old[i] = acc_w[w[i] >> 16];
+                old[i] = lds_f64(acc_w + 8u * (w[i] >> 16));
 #pragma unroll
             for (uint32_t i = 0; i < 4; i++)
                 if (i < nb)
-                    acc_w[w[i] >> 16] = old[i] + (double)p[i];
+                    sts_f64(acc_w + 8u * (w[i] >> 16), old[i] + (double)p[i]);
             __syncwarp();
             pos = end;
             R.release(pos);
         }
         if (lane == 0)
             sl_arrive(&empty[st]);   // this warp is done with the slab
+        if (++st == a.nxb) {
+            st = 0;
+            lap++;
+        }
     }
     // ---------------- results: rows straight to y, pieces of split rows to their carry slots
     const int32_t *rm = a.rowmap + bin * a.P;
     for (int i = lane; i < a.P; i += 32) {
         const int32_t r = rm[i];
         if (r >= 0)
-            store_y<MULTI>(y, r, acc_w[i], true);
+            store_y<MULTI>(y, r, lds_f64(acc_w + 8u * i), true);
         else if (r <= -2)
-            carry[-(r + 2)] = acc_w[i];
+            carry[-(r + 2)] = lds_f64(acc_w + 8u * i);
     }
 }
 
-// one thread per split row: add its pieces in piece order (deterministic)
+// one warp per split row: lanes add every 32nd piece, then a shuffle tree -- a fixed order: deterministic
 template <bool MULTI>
-__global__ void k_slab_fixup(const int32_t *__restrict__ split, int n_split, const double *__restrict__ carry, YOut y)
+__global__ void __launch_bounds__(256)
+k_slab_fixup(const int32_t *__restrict__ split, int n_split, const double *__restrict__ carry, YOut y)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= n_split)
         return;
     const int32_t row = split[3 * k], q0 = split[3 * k + 1], nq = split[3 * k + 2];
     double tot = 0.0;
-    for (int j = 0; j < nq; j++)
+    for (int j = lane; j < nq; j += 32)
         tot += carry[q0 + j];
-    store_y<MULTI>(y, row, tot, true);
+    tot = warp_sum(tot);
+    if (lane == 0)
+        store_y<MULTI>(y, row, tot, true);
 }
 
 template <typename VT, typename XT, bool MULTI>
@@ -898,7 +985,7 @@ static int slab_launch(StreamPlan *P, const SlArgs &a, const void *d_x, const YO
     }
     CSRK_LAUNCH(k, (unsigned)P->G, (unsigned)(P->NW + 1) * 32, P->smem_bytes, s, a, (const XT *)d_x, y, carry);
     if (P->n_split)
-        CSRK_LAUNCH((k_slab_fixup<MULTI>), (unsigned)div_up(P->n_split, 128), 128, 0, s, P->split, P->n_split, carry, y);
+        CSRK_LAUNCH((k_slab_fixup<MULTI>), (unsigned)div_up((int64_t)P->n_split * 32, 256), 256, 0, s, P->split, P->n_split, carry, y);
     return CSRK_OK;
 }
 
@@ -932,6 +1019,7 @@ int stream_run(csrk_matrix *h, StreamPlan *P, const void *d_x, const YOut &y, cu
     a.slab_bytes = P->slab_bytes;
     a.ring = P->ring;
     a.nst = P->nst;
+    a.nxb = P->nxb;
     a.ncols = h->ncols;
     // carry slots of the split rows: per call (concurrent calls on one handle must not share them)
     DevBuf carry;
