@@ -123,19 +123,19 @@ void dev_free(void *p, cudaStream_t s);
 
 // ------------------------------------------------------------------ matrix
 struct SpmvPlan;  // spmv.cu: tile map of the CSR kernel
-struct StreamPlan;  // spmv_stream.cu: slab-major re-layout of the entries for the slab-stream kernel
+struct StreamPlan;  // spmv_slab.cu: slab-major re-layout of the entries for the slab kernel
 struct YOut;        // spmv.cuh
 
 // tunables settable through csrk_set_option (tests force the slab path on small inputs)
 struct Options {
-    std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab-stream kernel
+    std::atomic<int64_t> spmv_mode{0};                  // 0 auto, 1 CSR tile kernel, 2 slab kernel
     std::atomic<int64_t> stream_min_nnz{4 * 1000 * 1000};  // auto: smallest nnz worth a stream plan
     std::atomic<int64_t> stream_slab_bytes{0};          // > 0: cap on the x slab size (tests force many slabs)
     std::atomic<int64_t> stream_ctas{0};                // > 0: CTAs (row groups) of the stream kernel instead of one per SM
     std::atomic<int64_t> stream_warps{16};              // consumer warps per CTA of the stream kernel (1..31)
-    std::atomic<int64_t> stream_piece{512};             // longest pseudo-row: longer rows are cut into interleaved pieces
+    std::atomic<int64_t> stream_piece{1024};             // longest pseudo-row: longer rows are cut into interleaved pieces
     std::atomic<int64_t> stream_ring_bytes{4096};       // per-warp prefetch ring of the entry stream (4096 | 8192)
-    std::atomic<int64_t> stream_ring_chunks{4};         // chunks (bulk copies) per ring: 2 | 4
+    std::atomic<int64_t> stream_ring_chunks{2};         // chunks (bulk copies) per ring: 2 | 4
     std::atomic<int64_t> stream_xbufs{2};               // x slabs resident per CTA: 2 | 3
     std::atomic<int64_t> radix_bits{0};                 // digit width of the stable sort: 0 = pick (9 when it saves a pass), 8, 9
     std::atomic<int64_t> spmv_zero_copy_y{1};           // csrk_spmv: store rows straight into pinned host y
@@ -182,6 +182,7 @@ void stream_info(const StreamPlan *p, int64_t *out /*[11]: G, NW, nslab, S, P, Q
 
 // ops implemented across the .cu files (all enqueue on `s`, no sync unless stated)
 int spmv_run(csrk_matrix *h, const void *d_x, int x_kind, double *d_y, cudaStream_t s);
+bool spmv_uses_slab(const csrk_matrix *h, int x_kind, const void *d_x);  // the slab kernel (spmv_slab.cu) will serve this call
 int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d_ys, int n_out, cudaStream_t s,
                    bool multicast = false);
 int mc_broadcast_run(void *mc_dst, const void *src, int64_t nbytes, cudaStream_t s);

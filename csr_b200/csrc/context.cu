@@ -368,7 +368,7 @@ int csrk_set_option(const char *name, int64_t value)
 {
     CSRK_ARG(name != nullptr, "option name is NULL");
     if (!strcmp(name, "spmv_mode")) {
-        CSRK_ARG(value >= 0 && value <= 2, "spmv_mode must be 0 (auto), 1 (CSR tile kernel) or 2 (slab-stream kernel)");
+        CSRK_ARG(value >= 0 && value <= 2, "spmv_mode must be 0 (auto), 1 (CSR tile kernel) or 2 (slab kernel)");
         options().spmv_mode = value;
     } else if (!strcmp(name, "stream_min_nnz")) {
         options().stream_min_nnz = value;
@@ -668,10 +668,11 @@ int csrk_spmv(csrk_h h, const void *x, int x_kind, double *y)
     CSRK_TRY(dy.alloc((size_t)h->nrows * 8, s));
     if (h->ncols)
         CSRK_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)h->ncols * x_kind, cudaMemcpyHostToDevice, s));
-    // y in pinned (mapped) host memory: the kernel stores every finished row straight into it over PCIe
-    // as a second output, so the 8 B/row device-to-host copy overlaps the compute instead of following it
+    // y in pinned (mapped) host memory: the tile kernel stores every finished row straight into it over PCIe
+    // as a second output, so the 8 B/row device-to-host copy overlaps the compute instead of following it.
+    // (The slab kernel finishes all rows at its very end, in bin order: a plain copy after it is faster.)
     double *y_mapped = nullptr;
-    if (h->nrows && h->nnz && options().spmv_zero_copy_y.load()) {
+    if (h->nrows && h->nnz && options().spmv_zero_copy_y.load() && !spmv_uses_slab(h, x_kind, dx.p)) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, y) == cudaSuccess) {
             if (at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)

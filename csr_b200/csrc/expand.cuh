@@ -1,5 +1,5 @@
 // expand.cuh -- two small building blocks shared by the stable transpose (transpose.cu) and the
-// SpMV stream-plan builder (spmv_stream.cu): the owning row of every nnz position, and segment
+// SpMV slab-plan builder (spmv_slab.cu): the owning row of every nnz position, and segment
 // bounds read off a sorted key array.
 #pragma once
 

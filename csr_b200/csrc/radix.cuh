@@ -1,6 +1,6 @@
 // radix.cuh -- hand-written stable LSD radix-sort pass (8- or 9-bit digits) over int32 keys with
 // an int32 payload and an optional value payload.  Used by the stable transpose /
-// order_columns (transpose.cu) and by the SpMV stream-plan builder (spmv_stream.cu).
+// order_columns (transpose.cu) and by the SpMV slab-plan builder (spmv_slab.cu).
 //
 //   k_radix_hist     per-tile digit histogram, written digit-major [digit][tile]
 //   exclusive_scan   over the flattened histogram -> global offset of every (digit, tile)

@@ -179,13 +179,16 @@ k_spmv_tile(int32_t nrows, int64_t nnz, const RPT *__restrict__ rp, const int32_
     }
 }
 
-// One thread per tile t >= 1.  If tile t is the FIRST continuation tile of the row
-// that spills into it, add that row's carries in tile order: deterministic.
+// One warp per tile t >= 1.  If tile t is the FIRST continuation tile of the row that spills into it, add
+// that row's carries: lanes take every 32nd tile, then a shuffle tree -- a fixed order, so deterministic
+// (a 1M-entry row has 244 carries: one thread adding them in sequence took 16 us of a 0.36 ms step).
 template <typename RPT, bool MULTI>
-__global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict__ rp,
-                             const int32_t *__restrict__ tile_row, const double *__restrict__ carry, YOut y)
+__global__ void __launch_bounds__(256)
+k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict__ rp,
+             const int32_t *__restrict__ tile_row, const double *__restrict__ carry, YOut y)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int64_t t = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1;
+    const int lane = threadIdx.x & 31;
     if (t >= ntiles)
         return;
     const int64_t base = t * SPMV_TILE;
@@ -199,9 +202,11 @@ __global__ void k_spmv_fixup(int64_t ntiles, int64_t nnz, const RPT *__restrict_
     const int64_t re = (int64_t)rp[row + 1];
     const int64_t tlast = (re - 1) / SPMV_TILE;
     double tot = 0.0;
-    for (int64_t u = t; u <= tlast; u++)
+    for (int64_t u = t + lane; u <= tlast; u += 32)
         tot += carry[u];
-    store_y<MULTI>(y, row, y.p[0][row] + tot, true);
+    tot = warp_sum(tot);
+    if (lane == 0)
+        store_y<MULTI>(y, row, y.p[0][row] + tot, true);
 }
 
 static int ensure_plan(csrk_matrix *h, cudaStream_t s, SpmvPlan **out)
@@ -249,14 +254,14 @@ static int launch_spmv(csrk_matrix *h, SpmvPlan *p, const void *d_x, YOut d_y, d
         CSRK_LAUNCH((k_spmv_tile<RPT, VT, XT, true>), (unsigned)p->ntiles, SPMV_BLOCK, 0, s, h->nrows, h->nnz,
                     (const RPT *)h->rp, h->ci, (const VT *)h->vs, (const XT *)d_x, d_y, p->tile_row, carry);
         if (p->ntiles > 1)
-            CSRK_LAUNCH((k_spmv_fixup<RPT, true>), (unsigned)div_up(p->ntiles - 1, 256), 256, 0, s, p->ntiles, h->nnz,
+            CSRK_LAUNCH((k_spmv_fixup<RPT, true>), (unsigned)div_up((p->ntiles - 1) * 32, 256), 256, 0, s, p->ntiles, h->nnz,
                         (const RPT *)h->rp, p->tile_row, carry, d_y);
         return CSRK_OK;
     }
     CSRK_LAUNCH((k_spmv_tile<RPT, VT, XT, false>), (unsigned)p->ntiles, SPMV_BLOCK, 0, s, h->nrows, h->nnz,
                 (const RPT *)h->rp, h->ci, (const VT *)h->vs, (const XT *)d_x, d_y, p->tile_row, carry);
     if (p->ntiles > 1)
-        CSRK_LAUNCH((k_spmv_fixup<RPT, false>), (unsigned)div_up(p->ntiles - 1, 256), 256, 0, s, p->ntiles, h->nnz,
+        CSRK_LAUNCH((k_spmv_fixup<RPT, false>), (unsigned)div_up((p->ntiles - 1) * 32, 256), 256, 0, s, p->ntiles, h->nnz,
                     (const RPT *)h->rp, p->tile_row, carry, d_y);
     return CSRK_OK;
 }
@@ -281,7 +286,7 @@ static int launch_spmv_v(csrk_matrix *h, SpmvPlan *p, const void *d_x, int x_kin
     }
 }
 
-// The slab-stream kernel (spmv_stream.cu) stages x in shared memory and reads a re-laid-out copy of the
+// The slab kernel (spmv_slab.cu) stages x in shared memory and reads a re-laid-out copy of the
 // entries; it pays G copies of x over the L2->SM fabric for never gathering x through L1/L2.  Auto mode
 // takes it when that trade wins: a matrix large enough to be worth a plan (one stable sort of the entries,
 // built on the first mult_vec of the handle) whose x, re-read once per SM, is smaller than its entry stream.
@@ -296,6 +301,13 @@ static bool stream_wanted(const csrk_matrix *h, int x_kind, const void *d_x)
         return false;
     const double reload = (double)ctx().sm_count * (double)h->ncols * x_kind;
     return reload <= (double)h->nnz * (4 + h->val_kind);
+}
+
+bool spmv_uses_slab(const csrk_matrix *h, int x_kind, const void *d_x)
+{
+    if (h->nrows == 0 || h->nnz == 0 || !stream_wanted(h, x_kind, d_x))
+        return false;
+    return !h->stream_failed[x_kind == 4 ? 0 : 1];
 }
 
 static int ensure_stream(csrk_matrix *h, int x_kind, StreamPlan **out)

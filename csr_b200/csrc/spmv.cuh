@@ -1,4 +1,4 @@
-// spmv.cuh -- pieces shared by the two SpMV kernels (spmv.cu: CSR tile kernel, spmv_stream.cu: slab-stream
+// spmv.cuh -- pieces shared by the two SpMV kernels (spmv.cu: CSR tile kernel, spmv_slab.cu: slab-stream
 // kernel): the value-less marker type, numba's product promotion and the (multi-destination) y store.
 #pragma once
 

@@ -99,7 +99,7 @@ class DistSpMV:
     """
 
     def __init__(self, local, row_counts, *, x_dtype="f4", device=None, group=None, compute=None, kernel=None,
-                 fused=False, chunks=1, nvls=True):
+                 fused=False, chunks=1, nvls=True, handle=None):
         import torch
         self.torch = torch
         self.group = group
@@ -115,10 +115,12 @@ class DistSpMV:
             torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
         tdt = torch.float32 if np.dtype(x_dtype) == np.float32 else torch.float64
         self.x = torch.zeros(self.ncols, dtype=tdt, device=self.device)
-        self.chunks = max(1, int(chunks)) if (self.world > 1 and not fused) else 1
+        self.chunks = max(1, int(chunks)) if (self.world > 1 and not fused and handle is None) else 1
         # chunk c of rank r holds rows [ccut[r][c], ccut[r][c+1]) of that rank's block; every rank needs all
         # ranks' chunk sizes to strip the padding, so they are exchanged once
-        my_cuts = partition_rows(local.rowptrs, self.chunks)
+        # (``handle``: the block already lives on the device -- e.g. generated there -- and ``local`` only carries
+        # its shape; ownership of the handle passes to this object)
+        my_cuts = [0, int(local.nrows)] if handle is not None else partition_rows(local.rowptrs, self.chunks)
         self.ccut = self._exchange_cuts(my_cuts)
         self.cpad = [max(self.ccut[r][c + 1] - self.ccut[r][c] for r in range(self.world)) for c in range(self.chunks)]
         self.coff = [0]
@@ -145,7 +147,9 @@ class DistSpMV:
                 from .kernels import get_kernel
                 kernel = get_kernel("cuda")
             self.kernel = kernel
-            if self.chunks == 1:
+            if handle is not None:
+                self.handles = [handle]
+            elif self.chunks == 1:
                 self.handles = [kernel.to_handle(local)]
             else:
                 self.handles = [kernel.to_handle(local.subset_rows(my_cuts[c], my_cuts[c + 1])) for c in range(self.chunks)]

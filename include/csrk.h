@@ -61,7 +61,7 @@ int csrk_device_info(int *sm_count, int64_t *mem_total, int64_t *mem_free, int *
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t csrk_launch_count(void);
 int csrk_synchronize(void);
-/* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 slab-stream kernel (x staged in shared memory);
+/* Tunables: "spmv_mode" 0 auto | 1 CSR tile kernel | 2 slab kernel (x staged in shared memory);
  * "stream_min_nnz" smallest nnz for which auto mode builds a stream plan;
  * "stream_slab_bytes" > 0 caps the x slab size, "stream_ctas" > 0 sets the number of CTAs (row groups),
  *               "stream_warps" 1..31 the consumer warps per CTA of the slab kernel, "stream_piece" 8..4096 the

@@ -1,5 +1,5 @@
 """
-GPU: the slab-stream SpMV kernel (csr_b200/csrc/spmv_stream.cu: x staged in shared memory, entries re-laid
+GPU: the slab-stream SpMV kernel (csr_b200/csrc/spmv_slab.cu: x staged in shared memory, entries re-laid
 out per warp and slab), forced on through the ``spmv_mode`` option so that small inputs exercise it --
 with small x slabs, few CTAs and few warps so that cells, pieces, carries and the block-to-block run
 hand-over all occur -- against the golden vectors, the oracle and the CSR tile kernel.

@@ -1,12 +1,7 @@
 #!/bin/bash
+# small-scale shake-out of every bench leg, then the default bench and the reference arm
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-N=${N:-1}
-if [ "$N" = "1" ]; then
-  timeout 1200 python bench.py --steps 100 --warmup 5 2> gpurun_out/bench_n1.err | tee gpurun_out/bench_n1.json
-  tail -4 gpurun_out/bench_n1.err
-else
-  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-     bench.py --gpus $N --steps 100 --warmup 5 2> gpurun_out/bench_n$N.err | tee gpurun_out/bench_n$N.json
-  tail -6 gpurun_out/bench_n$N.err
-fi
+echo "== small"; timeout 600 python bench.py --scale 0.05 --spgemm-scale 0.05 --cfg3-scale 0.01 --cfg3-products 1e7 --steps 20 > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err || { tail -20 gpurun_out/bench_small.err; exit 1; }
+echo "== full"; timeout 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -12 gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json | head -c 9000
+echo "== reference"; timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -3 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
