@@ -969,9 +969,13 @@ k_own_combine(const int32_t *__restrict__ rows, int nbin, const int *__restrict_
 //
 // Scale of row i: 2^(e0 - hb_i) with hb_i = ceil(log2(len_i + 1)) bits of headroom for the at most
 // len_i terms of one output element and 2^e0 * max|a*b| <= 2^62.  Every term is rounded once to a
-// multiple of 2^-(e0-hb_i); spgemm_run only takes this path when all values are finite, non-negative
-// and max|a*b| / min|a*b| <= 2^(26-hb), which bounds the relative error of every output element by
-// 2^-35 = 2.9e-11 (rtol 1e-10 of the parity contract); anything else takes the owner kernel.
+// multiple of 2^-(e0-hb_i), i.e. with an absolute error of at most 2^(hb-63) * max|a*b|.  spgemm_run only
+// takes this path when all values are finite and max|a*b| / min|a*b| <= 2^(26-hb): then every term's rounding
+// error is below 2^-37 of that term's own magnitude, and the error of an output element is below
+// 2^-35 * sum_k |a_ik||b_kj| = 2.9e-11 of the magnitude that was summed (rtol 1e-10 of the parity contract,
+// stated the way a re-ordered floating-point sum is bounded).  For non-negative operands that is the relative
+// error of the element itself; signs are welcome (two's-complement words), a wide dynamic range is not --
+// mean-centred ratings have values arbitrarily close to 0, so min|a*b| is tiny -- and takes the owner kernel.
 struct ValStats {
     unsigned long long min_bits, max_bits;  // bit patterns of the smallest non-zero and the largest |v|
     int negative, nonfinite;
@@ -1558,7 +1562,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                 CSRK_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
                 CSRK_CUDA(cudaStreamSynchronize(s));
                 owner = !bad;
-                if (owner && want_fixed && !vs_h[0].negative && !vs_h[1].negative && !vs_h[0].nonfinite && !vs_h[1].nonfinite &&
+                if (owner && want_fixed && !vs_h[0].nonfinite && !vs_h[1].nonfinite &&
                     vs_h[0].max_bits && vs_h[1].max_bits) {
                     double lim[4];
                     const unsigned long long bits[4] = {vs_h[0].min_bits, vs_h[0].max_bits, vs_h[1].min_bits, vs_h[1].max_bits};
@@ -1569,7 +1573,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                         hb++;  // ceil(log2(longest row + 1)): terms per output element
                     int x = 0;
                     (void)frexp(pmax, &x);  // pmax <= 2^x
-                    // relative error of an output element <= (pmax / pmin) * 2^(hb - 61); keep it below 2^-35
+                    // error of an output element <= (pmax / pmin) * 2^(hb - 61) * sum|terms|; keep it below 2^-35
                     if (hb <= 24 && passes <= FIX_MAX_PASSES && pmin > 1e-280 && pmax < 1e280 && pmax / pmin <= ldexp(1.0, 26 - hb)) {
                         fixed = true;
                         e0 = 62 - x;

@@ -32,7 +32,7 @@
 //   * pieces of split rows go to a carry array and a tiny fix-up kernel adds them in piece order.
 //
 // Cost model: HBM bytes are the stream + x once + y; the L2->SM fabric carries the stream
-// plus G copies of x, which is why auto mode only picks this kernel when G*ncols*X is below the stream size.
+// plus G copies of x, which is why auto mode only picks this kernel when G*ncols*X is below 1.6 x the stream size.
 #include <type_traits>
 
 #include "expand.cuh"
@@ -393,7 +393,10 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     const int64_t nnz = h->nnz;
     const int B = P->G * P->NW;
     if (nnz >= ((int64_t)1 << 31) - 64)
+    {
+        set_error("slab plan: nnz %lld needs 64-bit run ids", (long long)nnz);
         return CSRK_EOVERFLOW;   // run starts and run ids are 32-bit
+    }
 
     // 1. pseudo-rows
     DevBuf qbase;
@@ -411,7 +414,10 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     const size_t bar_bytes = (size_t)(2 * 3 + P->NW * SL_NST_MAX) * 8 + 16 + (size_t)P->ring;
     const size_t smem_max = ctx().smem_optin;
     if (P->P > 65534 || Q >= ((int64_t)1 << 31) || acc_bytes + ring_bytes + bar_bytes + (size_t)P->nxb * 4096 > smem_max)
+    {
+        set_error("slab plan: %lld pseudo-rows per warp do not fit shared memory", (long long)P->P);
         return CSRK_EOVERFLOW;  // too many rows for shared-memory accumulators: stay on the tile kernel
+    }
     // a buffer is one slab + 128 bytes (the always-zero slot the inert entries point at)
     int64_t slab = (int64_t)((smem_max - acc_bytes - ring_bytes - bar_bytes) / P->nxb - 128) & ~(int64_t)127;
     slab = std::min<int64_t>(slab, (int64_t)65408 * P->x_kind);   // columns inside a slab (and the zero slot) fit 16 bits
@@ -427,7 +433,10 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     const int64_t ncells = (int64_t)B * P->nslab;
     const int LB = sl_bits((int64_t)P->piece + 2);   // run lengths 1..piece (duplicate columns may exceed S)
     if (ncells >= ((int64_t)1 << (30 - LB)))
+    {
+        set_error("slab plan: %lld cells x %d length bits exceed the 31-bit run keys", (long long)ncells, LB);
         return CSRK_EOVERFLOW;   // (cell, length) run keys are 31-bit
+    }
 
     DevBuf qkey, qid, qdest, order, qbl, splitcnt;
     CSRK_TRY(qkey.alloc(sizeof(int32_t) * (size_t)Q, s));
@@ -528,7 +537,10 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     CSRK_CUDA(cudaMemcpyAsync(&P->n_split, splitcnt.as<int>(), sizeof(int), cudaMemcpyDeviceToHost, s));
     CSRK_CUDA(cudaStreamSynchronize(s));
     if (total / B + P->ring >= ((int64_t)1 << 31))
+    {
+        set_error("slab plan: a warp's stream of %lld bytes needs 64-bit positions", (long long)(total / B));
         return CSRK_EOVERFLOW;   // positions inside a bin's stream are 32-bit
+    }
     CSRK_TRACE_MARK("slab plan: streams written", s);
     return CSRK_OK;
 }
@@ -989,20 +1001,35 @@ static int slab_launch(StreamPlan *P, const SlArgs &a, const void *d_x, const YO
     return CSRK_OK;
 }
 
+// Rows leave the slab kernel at its very end and in bin order (scattered 8-byte stores): with several
+// destinations (the gather buffers of peer GPUs / an NVLink multicast address) the kernel writes the local y
+// only and the finished segment is copied out in one coalesced pass (measured on 2 B200: 8-byte multimem.st
+// from the kernel's epilogue cost 0.23 ms, the copy 0.02 ms).
 template <typename VT, typename XT>
-static int slab_launch_m(StreamPlan *P, const SlArgs &a, const void *d_x, const YOut &y, double *carry, cudaStream_t s)
+static int slab_launch_m(StreamPlan *P, const SlArgs &a, const void *d_x, const YOut &y, double *carry, cudaStream_t s,
+                         int32_t nrows)
 {
-    if (y.n > 1)
-        return slab_launch<VT, XT, true>(P, a, d_x, y, carry, s);
-    return slab_launch<VT, XT, false>(P, a, d_x, y, carry, s);
+    YOut local = y;
+    local.n = 1;
+    local.mc = 0;
+    CSRK_TRY((slab_launch<VT, XT, false>(P, a, d_x, local, carry, s)));
+    if (y.n > 1) {
+        const size_t bytes = (size_t)nrows * 8;
+        if (y.mc)
+            return mc_broadcast_run(y.p[1], y.p[0], (int64_t)bytes, s);
+        for (int k = 1; k < y.n; k++)
+            CSRK_CUDA(cudaMemcpyAsync(y.p[k], y.p[0], bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    return CSRK_OK;
 }
 
 template <typename VT>
-static int slab_launch_x(StreamPlan *P, const SlArgs &a, const void *d_x, const YOut &y, double *carry, cudaStream_t s)
+static int slab_launch_x(StreamPlan *P, const SlArgs &a, const void *d_x, const YOut &y, double *carry, cudaStream_t s,
+                         int32_t nrows)
 {
     if (P->x_kind == 4)
-        return slab_launch_m<VT, float>(P, a, d_x, y, carry, s);
-    return slab_launch_m<VT, double>(P, a, d_x, y, carry, s);
+        return slab_launch_m<VT, float>(P, a, d_x, y, carry, s, nrows);
+    return slab_launch_m<VT, double>(P, a, d_x, y, carry, s, nrows);
 }
 
 int stream_run(csrk_matrix *h, StreamPlan *P, const void *d_x, const YOut &y, cudaStream_t s)
@@ -1026,9 +1053,9 @@ int stream_run(csrk_matrix *h, StreamPlan *P, const void *d_x, const YOut &y, cu
     if (P->n_split)
         CSRK_TRY(carry.alloc(sizeof(double) * (size_t)P->Q, s));
     switch (h->val_kind) {
-    case 4: return slab_launch_x<float>(P, a, d_x, y, carry.as<double>(), s);
-    case 8: return slab_launch_x<double>(P, a, d_x, y, carry.as<double>(), s);
-    default: return slab_launch_x<NoVal>(P, a, d_x, y, carry.as<double>(), s);
+    case 4: return slab_launch_x<float>(P, a, d_x, y, carry.as<double>(), s, h->nrows);
+    case 8: return slab_launch_x<double>(P, a, d_x, y, carry.as<double>(), s, h->nrows);
+    default: return slab_launch_x<NoVal>(P, a, d_x, y, carry.as<double>(), s, h->nrows);
     }
 }
 

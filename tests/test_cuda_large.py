@@ -285,14 +285,38 @@ def test_item_item_fixed_point_path(kernel, dtype):
     assert np.allclose(chunked.values, vs, rtol=1e-10, atol=0.0)
 
 
-@pytest.mark.parametrize("case", ["negative", "wide_range", "nonfinite"])
-def test_fixed_point_gate_falls_back_to_owner(kernel, case):
-    """The fixed-point kernel is only taken when its error bound holds: mixed signs, a wide dynamic range or a
-    non-finite value send the heavy rows to the owner-computes kernel (bit-identical to the oracle)."""
+def test_fixed_point_signed_values(kernel):
+    """Mixed signs with a bounded range of magnitudes take the fixed-point kernel (two's-complement words): every
+    element within 1e-10 of the magnitude that was summed, sum_k |a_ik||b_kj| -- the bound of a re-ordered sum --
+    and the result does not depend on the chunking."""
     R = synth.powerlaw_csr(16000, 12000, 1_600_000, seed=81, dtype="f8", alpha=0.5, cap=600, min_len=20, col_skew=2.0)
     v = R.values.copy()
-    if case == "negative":
-        v[::7] *= -1.0
+    v[::7] *= -1.0
+    v[1::3] *= -1.0
+    M = CSR(R.nrows, R.ncols, R.nnz, R.rowptrs, R.colinds, v).transpose()
+    ref = orc.mult_abt(M, M)
+    rp, ci, vs = canonical(ref)
+    terms = spgemm_terms(M, M, transpose=True)
+    got, st = _abt(kernel, M)
+    assert st["dense_path"] == "fixed"
+    assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
+    assert_values_close(got.values, vs, 1e-10, terms)
+    chunked, st2 = _abt(kernel, M, own_chunk_prod=30000)
+    heavy = np.repeat(np.diff(rp) > 8192, np.diff(rp))      # the rows of the dense (fixed-point) path
+    assert st2["dense_path"] == "fixed" and np.array_equal(chunked.values[heavy], got.values[heavy])
+
+
+@pytest.mark.parametrize("case", ["wide_range", "nonfinite", "centred"])
+def test_fixed_point_gate_falls_back_to_owner(kernel, case):
+    """The fixed-point kernel is only taken when its error bound holds: a wide dynamic range (mean-centred ratings
+    have values arbitrarily close to zero) or a non-finite value send the heavy rows to the owner-computes
+    kernel (bit-identical to the oracle)."""
+    R = synth.powerlaw_csr(16000, 12000, 1_600_000, seed=81, dtype="f8", alpha=0.5, cap=600, min_len=20, col_skew=2.0)
+    v = R.values.copy()
+    if case == "centred":
+        lens = np.diff(R.rowptrs)
+        means = np.add.reduceat(v, R.rowptrs[:-1].astype(np.int64)) / np.maximum(lens, 1)
+        v = v - np.repeat(means, lens)
     elif case == "wide_range":
         v[::5] *= 1e-7
     else:

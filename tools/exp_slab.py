@@ -13,7 +13,9 @@ def _cfg(c):
 cfgs = [_cfg(c) for c in (sys.argv[2] if len(sys.argv) > 2 else "16").split(",")]
 skew = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 t0 = time.time()
-A = synth.cfg2_spmv(scale, col_skew=skew); x = synth.dense_vector(A.ncols, 77, "f4")
+colmul = int(sys.argv[4]) if len(sys.argv) > 4 else 1    # a rank's block of the weak-scaled matrix: colmul x the columns
+n = max(int(1_000_000 * scale), 64)
+A = synth.powerlaw_csr(n, n * colmul, 100 * n, seed=2, dtype="f4", alpha=1.0, col_skew=skew); x = synth.dense_vector(A.ncols, 77, "f4")
 print(f"gen {time.time()-t0:.1f}s {A}", flush=True)
 xd = torch.from_numpy(x).cuda(); yd = torch.zeros(A.nrows, dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
