@@ -366,8 +366,10 @@ def bench_spmv_headline(args, env):
     if want_nvls and ds.nvls is None:
         log(f"[rank {rank}] NVLS path unavailable ({getattr(ds, 'nvls_error', '?')}); using the NCCL collectives")
     ds.set_x(x_host)
+    ds.local_spmv()                  # first call of the handle: CSR tile kernel (one-shot handles never build a plan)
+    torch.cuda.synchronize()
     t0p = time.perf_counter()
-    ds.local_spmv()                  # the first call builds the SpMV plan of the handle
+    ds.local_spmv()                  # second call: builds the slab plan when auto mode selects that kernel
     torch.cuda.synchronize()
     t_plan = time.perf_counter() - t0p
     t_handle = time.perf_counter() - t0
@@ -376,6 +378,12 @@ def bench_spmv_headline(args, env):
 
     local_bytes = ds.bytes_per_step(A.nnz, 4)
     total_bytes = allsum(float(local_bytes))
+    graphed = False
+    if world > 1 and args.graph != "off":
+        graphed = allsum(1.0 if ds.capture() else 0.0) == world      # all ranks or none
+        if not graphed:
+            ds._graph = None
+            log(f"[rank {rank}] step not captured in a CUDA graph: {getattr(ds, 'graph_error', '?')}")
 
     # ---- value: device-resident, whole step (broadcast + SpMV + all-gather)
     for _ in range(W):
@@ -432,7 +440,9 @@ def bench_spmv_headline(args, env):
             t_b = timed(bcast)
             t_bar = timed(lambda: ds.nvls[0].barrier())
             coll = {"multicast_broadcast_x_plus_barrier_ms": round(t_b, 5), "broadcast_x_bytes": nb,
-                    "barrier_ms": round(t_bar, 5), "gather_y": "inside the SpMV kernel (multimem.st per finished row)",
+                    "barrier_ms": round(t_bar, 5),
+                    "gather_y": "one multicast copy of the y segment after the slab kernel" if kname.startswith("k_spmv_slab")
+                    else "inside the SpMV kernel (multimem.st per finished row)",
                     "note": "NVLink multicast through the NVSwitch (symmetric memory), timed alone"}
         elif ds.symm is None:
             t_b = timed(lambda: dist.broadcast(ds.x, src=0))
@@ -491,8 +501,11 @@ def bench_spmv_headline(args, env):
     if world == 1:
         par = f"single GPU: step = the local SpMV ({kname})"
     elif ds.nvls is not None:
-        par = (f"row-partitioned x{world}; step = NVLS multicast copy of x (root) + barrier + SpMV kernel storing each "
-               "finished y row once through the NVLink multicast address (fused gather) + barrier")
+        par = (f"row-partitioned x{world}; step = NVLS multicast copy of x (root) + barrier + " +
+               ("SpMV slab kernel + one coalesced copy of the finished y segment to the NVLink multicast address"
+                if kname.startswith("k_spmv_slab") else
+                "SpMV kernel storing each finished y row once through the NVLink multicast address (fused gather)") +
+               " + barrier" + ("; the whole step is one CUDA graph launch" if graphed else ""))
     elif ds.symm is not None:
         par = (f"row-partitioned x{world}; step = NCCL broadcast(x) + SpMV kernel storing y rows into every rank's "
                "buffer over NVLink (fused gather) + barrier")
@@ -970,6 +983,12 @@ def bench_cfg4(args, env):
     x_host = np.random.default_rng(79).standard_normal(ncols).astype(np.float32)
     ds.set_x(x_host)
     steps = max(env["steps"] // 4, 10)
+    ds.local_spmv()
+    ds.local_spmv()
+    torch.cuda.synchronize()
+    graphed = args.graph != "off" and allsum(1.0 if ds.capture() else 0.0) == world
+    if not graphed:
+        ds._graph = None
     for _ in range(3):
         ds.step()
     env["barrier"]()
@@ -1004,7 +1023,8 @@ def bench_cfg4(args, env):
             "value": round(total / ms / 1e6, 1), "unit": "GB/s", "ms_per_step": round(ms, 5), "kernel_ms": round(ms_k, 5),
             "kernel": kname, "per_gpu_frac_of_peak": round(local_bytes / ms_k / 1e6 / env["peak"], 4),
             "x_bytes": ncols * 4, "y_bytes": ncols * 8, "gen_s": round(t_gen, 1),
-            "parallelism": "NVLS multicast of x + in-kernel multicast gather of y" if ds.nvls is not None else "NCCL broadcast(x) + all-gather(y)",
+            "parallelism": ("NVLS multicast of x + in-kernel multicast gather of y" + (", one CUDA graph per step" if graphed else ""))
+            if ds.nvls is not None else "NCCL broadcast(x) + all-gather(y)",
             "parity": "every rank: " + ptxt}
 
 
@@ -1059,6 +1079,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=1, help="N>1: row chunks whose all-gathers overlap the next chunk's SpMV")
     ap.add_argument("--nvls", choices=["auto", "on", "off"], default="auto",
                     help="N>1: NVLink-multicast broadcast + in-kernel multicast gather (default when the box supports it)")
+    ap.add_argument("--graph", choices=["on", "off"], default="on", help="N>1: capture the step in a CUDA graph")
     ap.add_argument("--fused", action="store_true", help="fused SpMV+gather over peer memory instead of the NCCL all-gather")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the SpMV kernel, if known")
     args = ap.parse_args()

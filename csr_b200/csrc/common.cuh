@@ -162,6 +162,7 @@ struct csrk_matrix {
     csrk::SpmvPlan *plan = nullptr;  // lazily built SpMV tile map
     csrk::StreamPlan *stream[2] = {nullptr, nullptr};  // lazily built stream plans for float32 / float64 x
     bool stream_failed[2] = {false, false};
+    std::atomic<int> spmv_calls{0};  // auto mode builds the slab plan on the SECOND mult_vec: one-shot handles never pay for it
     std::mutex mu;
 };
 

@@ -301,6 +301,10 @@ static bool stream_wanted(const csrk_matrix *h, int x_kind, const void *d_x)
         return true;
     if (h->nnz < options().stream_min_nnz.load())
         return false;
+    // CSR.mult_vec of the reference makes a handle per call (csr/csr.py:582): a plan (10-60 ms) only pays for
+    // handles that are used again, so the first call of a handle stays on the tile kernel
+    if (h->spmv_calls.load(std::memory_order_relaxed) < 1 && !h->stream[x_kind == 4 ? 0 : 1])
+        return false;
     // measured on 1M-row blocks of 100M nnz: x of 4 MB (reload = 0.7 x the stream) 0.193 ms against 0.362 ms for the
     // tile kernel, 8 MB (1.5 x) 0.260 against 0.366; 16 MB and more stay on the tile kernel
     const double reload = (double)ctx().sm_count * (double)h->ncols * x_kind;
@@ -352,7 +356,9 @@ int spmv_run_multi(csrk_matrix *h, const void *d_x, int x_kind, double *const *d
             CSRK_LAUNCH(k_zero_f64, (unsigned)div_up(h->nrows, 256), 256, 0, s, d_ys[k], (int64_t)h->nrows);
         return CSRK_OK;
     }
-    if (stream_wanted(h, x_kind, d_x)) {
+    const bool slab = stream_wanted(h, x_kind, d_x);
+    h->spmv_calls.fetch_add(1, std::memory_order_relaxed);
+    if (slab) {
         StreamPlan *sp = nullptr;
         CSRK_TRY(ensure_stream(h, x_kind, &sp));
         if (sp)

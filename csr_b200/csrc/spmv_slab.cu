@@ -42,7 +42,8 @@
 namespace csrk {
 
 constexpr int SL_TB = 8;                   // steps per J group
-constexpr int SL_HDR = 160;                // J group header: 32 x (row << 16 | steps << 8 | len), 16 x u16 byte offsets
+constexpr int SL_NP = SL_TB / 2;           // pair-steps per J group: a lane reads two entries of its run at a time
+constexpr int SL_HDR = 144;                // J group header: 32 x (row << 16 | pair-steps << 8 | my pairs), 8 x u16 byte offsets
 constexpr int SL_NST_MAX = 4;              // chunks per ring: 2 or 4
 constexpr int SL_MAX_WARPS = 31;           // consumer warps (+1 producer warp = 1024 threads)
 
@@ -290,7 +291,7 @@ k_sl_item_bytes(int64_t NI, const int64_t *__restrict__ itembase, int64_t ncells
         bytes = 0;
         int nsub = 0;
         for (int t0 = 0; t0 < T; t0 += SL_TB, nsub++) {
-            const int n = warp_sum(min(max(len - t0, 0), SL_TB));
+            const int n = 2 * warp_sum((min(max(len - t0, 0), SL_TB) + 1) >> 1);   // odd runs end in a null entry
             bytes += SL_HDR + sl_pad16(2u * n) + sl_pad16((uint32_t)VB * n);
         }
         if (lane == 0)
@@ -336,28 +337,34 @@ k_sl_fill(int64_t NI, const int64_t *__restrict__ itembase, int64_t ncells, cons
     const uint32_t row = have ? ((uint32_t)spacked[start] >> 16) : (uint32_t)P;
     const int32_t T = __shfl_sync(0xffffffffu, len, 0);
     for (int t0 = 0; t0 < T; t0 += SL_TB) {
-        const int lk = min(max(len - t0, 0), SL_TB);
-        const int Tk = min(T - t0, SL_TB);
-        const int n = warp_sum(lk);
-        reinterpret_cast<uint32_t *>(o)[lane] = row << 16 | (uint32_t)Tk << 8 | (uint32_t)lk;
-        // byte offsets of steps 1..7 inside the column and value sections; slot 7 of the first eight = n
+        const int lk = min(max(len - t0, 0), SL_TB);       // my entries in this group
+        const int pk = (lk + 1) >> 1;                      // ... as pairs; an odd run ends in a null entry
+        const int Tp = (min(T - t0, SL_TB) + 1) >> 1;      // pair-steps of the group
+        const int n = 2 * warp_sum(pk);
+        reinterpret_cast<uint32_t *>(o)[lane] = row << 16 | (uint32_t)Tp << 8 | (uint32_t)pk;
+        // byte offsets of pair-steps 1..3 inside the column section, n, the same inside the value section, 0
         uint16_t *offs = reinterpret_cast<uint16_t *>(o + 128);
-        uint16_t *cols = reinterpret_cast<uint16_t *>(o + SL_HDR);
+        uint32_t *cols = reinterpret_cast<uint32_t *>(o + SL_HDR);     // two 16-bit columns per pair
         unsigned char *vals = o + SL_HDR + sl_pad16(2u * n);
-        int off = 0;
-        for (int t = 0; t < SL_TB; t++) {
-            const bool act = t < lk;
+        int off = 0;   // pairs before this pair-step
+        for (int t = 0; t < SL_NP; t++) {
+            const bool act = t < pk;
             const unsigned bal = __ballot_sync(0xffffffffu, act);
             if (act) {
-                const int32_t src = start + t0 + t;
-                cols[off + lane] = (uint16_t)((uint32_t)spacked[src] & 0xffffu);
-                if constexpr (VB > 0)
-                    reinterpret_cast<VT *>(vals)[off + lane] = svals[src];
+                const int32_t src = start + t0 + 2 * t;
+                const bool two = 2 * t + 1 < lk;
+                const uint32_t c0 = (uint32_t)spacked[src] & 0xffffu;
+                const uint32_t c1 = two ? ((uint32_t)spacked[src + 1] & 0xffffu) : (uint32_t)S;   // null: the zero x slot
+                cols[off + lane] = c0 | c1 << 16;
+                if constexpr (VB > 0) {
+                    reinterpret_cast<VT *>(vals)[2 * (off + lane)] = svals[src];
+                    reinterpret_cast<VT *>(vals)[2 * (off + lane) + 1] = two ? svals[src + 1] : VT(0);
+                }
             }
             off += __popc(bal);
             if (lane == 0) {
-                offs[t] = (uint16_t)(t < SL_TB - 1 ? 2 * off : off);   // offs[7] = n
-                offs[8 + t] = (uint16_t)(t < SL_TB - 1 ? VB * off : 0);
+                offs[t] = (uint16_t)(t < SL_NP - 1 ? 4 * off : n);            // offs[3] = n
+                offs[4 + t] = (uint16_t)(t < SL_NP - 1 ? 2 * VB * off : 0);
             }
         }
         o += SL_HDR + sl_pad16(2u * n) + sl_pad16((uint32_t)VB * n);
@@ -411,7 +418,7 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     // accumulators + nxb x slabs
     const size_t acc_bytes = (size_t)P->NW * (P->P + 1) * 8;
     const size_t ring_bytes = (size_t)P->NW * P->ring;
-    const size_t bar_bytes = (size_t)(2 * 3 + P->NW * SL_NST_MAX) * 8 + 16 + (size_t)P->ring;
+    const size_t bar_bytes = (size_t)(2 * 3 + P->NW * SL_NST_MAX) * 8 + 48 + (size_t)P->ring;
     const size_t smem_max = ctx().smem_optin;
     if (P->P > 65534 || Q >= ((int64_t)1 << 31) || acc_bytes + ring_bytes + bar_bytes + (size_t)P->nxb * 4096 > smem_max)
     {
@@ -778,22 +785,56 @@ __device__ __forceinline__ double sl_keep(double v, bool keep)
     return __longlong_as_double(keep ? __double_as_longlong(v) : 0ll);
 }
 
-// steps T0..T1-1 of a J group, fully predicated (no branches): the loads of all steps are independent.
-// co[t] / vo[t] = byte offset of step t inside the column / value section; lane l's entry is the l-th there.
-// A lane past the end of its run reads the ZERO PAD instead (column S = the always-zero x slot, value 0):
-// its term is exactly 0 whatever the other lanes' entries hold.
+// two values of a lane's pair
+template <typename T> struct SlPair {
+    T a, b;
+};
+template <typename T> __device__ __forceinline__ SlPair<T> lds_pair(uint32_t addr);
+template <> __device__ __forceinline__ SlPair<float> lds_pair<float>(uint32_t addr)
+{
+    SlPair<float> p;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(p.a), "=f"(p.b) : "r"(addr));
+    return p;
+}
+template <> __device__ __forceinline__ SlPair<double> lds_pair<double>(uint32_t addr)
+{
+    SlPair<double> p;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(p.a), "=d"(p.b) : "r"(addr));
+    return p;
+}
+template <typename VT, typename XT>
+__device__ __forceinline__ typename SlTerm<VT, XT>::type sl_mul(VT v, XT xv)
+{
+    using PT = typename SlTerm<VT, XT>::type;
+    if constexpr (std::is_same<PT, float>::value)
+        return __fmul_rn((float)xv, (float)v);
+    else
+        return __dmul_rn((double)xv, (double)v);
+}
+
+// pair-steps T0..T1-1 of a J group, fully predicated (no branches): the loads of all steps are independent.
+// co[t] / vo[t] = byte offset of pair-step t inside the column / value section; lane l's pair is the l-th there.
+// A lane past the end of its run reads the ZERO PAD instead (columns S = the always-zero x slot, values 0): its
+// terms are exactly 0 whatever the other lanes' entries hold.  The null entry that ends an odd run is the same.
 template <int T0, int T1, typename VT, typename XT>
-__device__ __forceinline__ void sl_steps(const SlRing &R, const int lk, const uint32_t cl, const uint32_t vl,
-                                         const uint32_t (&co)[SL_TB], const uint32_t (&vo)[SL_TB], const uint32_t xs,
+__device__ __forceinline__ void sl_steps(const SlRing &R, const int pk, const uint32_t cl, const uint32_t vl,
+                                         const uint32_t (&co)[SL_NP], const uint32_t (&vo)[SL_NP], const uint32_t xs,
                                          const uint32_t zpad, double &sum)
 {
 #pragma unroll
     for (int t = T0; t < T1; t++) {
-        const bool act = t < lk;
-        const uint32_t ca = act ? R.addr(cl + co[t]) : zpad;
-        const uint32_t va = act ? R.addr(vl + vo[t]) : zpad + 8u;
-        const XT xv = lds_val<XT>(xs + lds_u16(ca) * (uint32_t)sizeof(XT));
-        sum += (double)sl_term<VT, XT>(va, xv);
+        const bool act = t < pk;
+        const uint32_t cc = lds_u32(act ? R.addr(cl + co[t]) : zpad);
+        const XT x0 = lds_val<XT>(xs + (cc & 0xffffu) * (uint32_t)sizeof(XT));
+        const XT x1 = lds_val<XT>(xs + (cc >> 16) * (uint32_t)sizeof(XT));
+        if constexpr (std::is_same<VT, NoVal>::value) {
+            sum += (double)x0;
+            sum += (double)x1;
+        } else {
+            const SlPair<VT> v = lds_pair<VT>(act ? R.addr(vl + vo[t]) : zpad + 16u);
+            sum += (double)sl_mul<VT, XT>(v.a, x0);
+            sum += (double)sl_mul<VT, XT>(v.b, x1);
+        }
     }
 }
 
@@ -807,8 +848,9 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
     uint64_t *bars = reinterpret_cast<uint64_t *>(sl_smem);   // full[nxb], empty[nxb], ring[NW][nst], zero pad
     uint64_t *full = bars, *empty = bars + a.nxb, *rbar = bars + 2 * a.nxb;
     const uint32_t smem0 = sl_u32(sl_smem);
-    const uint32_t zpad = smem0 + (uint32_t)(2 * a.nxb + a.NW * a.nst) * 8u;   // 16 bytes: u16 column S, 8 zero bytes
-    const uint32_t ring0 = (zpad + 16u + (uint32_t)a.ring - 1u) & ~((uint32_t)a.ring - 1u);
+    // zero pad, 32 bytes at a 16-byte boundary: a column pair (S, S), then 16 zero bytes (a value pair)
+    const uint32_t zpad = (smem0 + (uint32_t)(2 * a.nxb + a.NW * a.nst) * 8u + 15u) & ~15u;
+    const uint32_t ring0 = (zpad + 32u + (uint32_t)a.ring - 1u) & ~((uint32_t)a.ring - 1u);
     const uint32_t xstride = (uint32_t)a.slab_bytes + 128u;                            // slab + the zero slot
     const uint32_t xbuf0 = ring0 + (uint32_t)a.NW * (uint32_t)a.ring;
     unsigned char *xbuf = sl_smem + (xbuf0 - smem0);
@@ -827,7 +869,9 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
     if (tid < a.nxb)
         reinterpret_cast<XT *>(xbuf + tid * xstride)[a.S] = XT(0);   // what the inert entries multiply
     if (tid == 32)
-        *reinterpret_cast<uint4 *>(sl_smem + (zpad - smem0)) = make_uint4((uint32_t)a.S, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sl_smem + (zpad - smem0)) = make_uint4((uint32_t)a.S | (uint32_t)a.S << 16, 0u, 0u, 0u);
+    if (tid == 33)
+        *reinterpret_cast<uint4 *>(sl_smem + (zpad + 16u - smem0)) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();   // the only CTA-wide barrier
     // CTA g walks the slabs starting at slab g*nslab/G and wraps around, so that at any moment the CTAs pull
     // different parts of x out of L2
@@ -899,22 +943,20 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
 #pragma unroll 1
         for (uint32_t j = 0; j < hdr.x; j++) {
             R.ensure(pos + SL_HDR);
-            const uint32_t m = lds_u32(R.addr(pos + 4u * lane));   // row << 16 | steps << 8 | my entries
-            const uint4 oc = lds_u32x4(R.addr(pos + 128)), ov = lds_u32x4(R.addr(pos + 144));
-            const uint32_t co[SL_TB] = {0u,         oc.x & 0xffffu, oc.x >> 16,     oc.y & 0xffffu,
-                                        oc.y >> 16, oc.z & 0xffffu, oc.z >> 16,     oc.w & 0xffffu};
-            const uint32_t vo[SL_TB] = {0u,         ov.x & 0xffffu, ov.x >> 16,     ov.y & 0xffffu,
-                                        ov.y >> 16, ov.z & 0xffffu, ov.z >> 16,     ov.w & 0xffffu};
-            const uint32_t n = oc.w >> 16;
+            const uint32_t m = lds_u32(R.addr(pos + 4u * lane));   // row << 16 | pair-steps << 8 | my pairs
+            const uint4 o = lds_u32x4(R.addr(pos + 128));
+            const uint32_t co[SL_NP] = {0u, o.x & 0xffffu, o.x >> 16, o.y & 0xffffu};
+            const uint32_t vo[SL_NP] = {0u, o.z & 0xffffu, o.z >> 16, o.w & 0xffffu};
+            const uint32_t n = o.y >> 16;
             const uint32_t vsec = pos + SL_HDR + sl_pad16(2u * n);
-            const uint32_t cl = pos + SL_HDR + 2u * lane, vl = vsec + VB * lane;
+            const uint32_t cl = pos + SL_HDR + 4u * lane, vl = vsec + 2u * VB * lane;
             const uint32_t end = vsec + sl_pad16(VB * n);
             R.ensure(end);
             const int lk = (int)(m & 0xffu);
             double sum = 0.0;
-            sl_steps<0, 6, VT, XT>(R, lk, cl, vl, co, vo, xs, zpad, sum);
-            if (((m >> 8) & 0xffu) > 6)
-                sl_steps<6, SL_TB, VT, XT>(R, lk, cl, vl, co, vo, xs, zpad, sum);
+            sl_steps<0, 3, VT, XT>(R, lk, cl, vl, co, vo, xs, zpad, sum);
+            if (((m >> 8) & 0xffu) > 3)
+                sl_steps<3, SL_NP, VT, XT>(R, lk, cl, vl, co, vo, xs, zpad, sum);
             if (lk) {
                 const uint32_t aa = acc_w + 8u * (m >> 16);
                 sts_f64(aa, lds_f64(aa) + sum);

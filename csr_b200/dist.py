@@ -248,9 +248,45 @@ class DistSpMV:
         else:  # injected compute (CPU tests): it is told which rows to produce
             self.compute(self.x, seg, self._my_cuts[c], self._my_cuts[c + 1])
 
+    def capture(self, broadcast_x: bool = True) -> bool:
+        """Capture one step into a CUDA graph (the multicast path only: its launches -- the copy of x, the
+        symmetric-memory barriers, the SpMV kernels, the copy-out of y -- are all plain stream work); ``step()``
+        then replays the graph: one launch per step instead of five to seven, so a slow host launch path cannot
+        open gaps around a 0.2-0.4 ms kernel.  Every rank must call it; returns False (and keeps the eager step)
+        if the capture fails -- ``graph_error`` says why."""
+        self._graph = None
+        if self.nvls is None or self.device.type != "cuda":
+            self.graph_error = "only the NVLS path is captured"
+            return False
+        torch = self.torch
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):               # warm-up on the capture side: plans, pools, barrier pads
+                    self._step_eager(broadcast_x)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_eager(broadcast_x)
+            self._graph, self._graph_bx = g, broadcast_x
+            return True
+        except Exception as e:
+            self._graph = None
+            self.graph_error = repr(e)
+            return False
+
     def step(self, broadcast_x: bool = True):
         """One distributed SpMV; the gather buffer then holds every rank's rows
         (``result()`` strips the padding)."""
+        g = getattr(self, "_graph", None)
+        if g is not None and self._graph_bx == broadcast_x:
+            g.replay()
+            return self.ybuf
+        return self._step_eager(broadcast_x)
+
+    def _step_eager(self, broadcast_x: bool = True):
         dist = _dist()
         if self.nvls is not None:
             hy, hx = self.nvls

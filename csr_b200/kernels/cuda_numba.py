@@ -40,6 +40,7 @@ def _bind(name, *argtypes):
     return f
 
 
+_create = _bind("csrk_create", C.c_int32, C.c_int32, C.c_int64, _P, C.c_int, _P, _P, C.c_int, _P)
 _dims = _bind("csrk_dims", _P, _P, _P, _P, _P, _P)
 _export = _bind("csrk_export", _P, _P, _P, _P)
 _spmv = _bind("csrk_spmv", _P, _P, C.c_int, _P)
@@ -59,6 +60,45 @@ def dims(h):
     if rc != 0:
         raise ValueError("invalid cuda kernel handle")
     return a32[0], a32[1], a64[0], ai[0], ai[1]
+
+
+@njit(nogil=True)
+def _create_checked(nrows, ncols, nnz, rp_ptr, rp_is64, ci_ptr, vs_ptr, val_kind):
+    out = np.zeros(1, np.uintp)
+    rc = _create(nrows, ncols, nnz, rp_ptr, rp_is64, ci_ptr, vs_ptr, val_kind, out.ctypes.data)
+    if rc == 1:
+        raise ValueError("to_handle: bad argument")
+    if rc == 2:
+        raise MemoryError("to_handle: out of device memory")
+    if rc != 0:
+        raise RuntimeError("to_handle failed")
+    return out[0]
+
+
+@njit(nogil=True)
+def create(nrows, ncols, nnz, rowptrs, colinds, values):
+    """to_handle from nopython code (numba/__init__.py:16-27): the six fields of the CSR record
+    (csr/_struct.py:10-28) are copied to the device; returns a RAW handle the caller releases.  The copies
+    are complete when this returns, so the arrays need not outlive the call."""
+    rp = np.ascontiguousarray(rowptrs)
+    ci = np.ascontiguousarray(colinds)
+    vs = np.ascontiguousarray(values)
+    h = _create_checked(nrows, ncols, nnz, rp.ctypes.data, 1 if rp.itemsize == 8 else 0, ci.ctypes.data, vs.ctypes.data,
+                        vs.itemsize)
+    if rp.shape[0] + ci.shape[0] + vs.shape[0] < 0:   # keeps rp / ci / vs alive across the native call
+        h = np.uintp(0)
+    return h
+
+
+@njit(nogil=True)
+def create_structure(nrows, ncols, nnz, rowptrs, colinds):
+    "``create`` for a CSR without values (values is None: the kernels use 1)."
+    rp = np.ascontiguousarray(rowptrs)
+    ci = np.ascontiguousarray(colinds)
+    h = _create_checked(nrows, ncols, nnz, rp.ctypes.data, 1 if rp.itemsize == 8 else 0, ci.ctypes.data, 0, 0)
+    if rp.shape[0] + ci.shape[0] < 0:
+        h = np.uintp(0)
+    return h
 
 
 def _kernel_vector(x):  # pragma: no cover - replaced by the overload below in nopython code

@@ -155,3 +155,45 @@ h = K.to_handle(A); c = K.from_handle(h); K.release_handle(h); K.release_handle(
 assert type(c) is CSR and (c.nrows, c.ncols, c.nnz) == (A.nrows, A.ncols, A.nnz)
 assert np.array_equal(c.rowptrs, A.rowptrs) and np.array_equal(c.colinds, A.colinds) and np.array_equal(c.values, A.values)
 """, env_extra={"CSR_KERNEL": "cuda"}))
+
+
+@pytest.mark.gpu
+def test_reference_nopython_callers_reach_cuda():
+    """``CSR_KERNEL=cuda`` serves the STATIC kernel path too: ``csr/kernel.py:9-16`` binds the cuda functions and the
+    ``@overload_method``s of csr/_wiring.py:116-151 call them from ``@njit`` code on ``CSRType`` structrefs
+    (to_handle -> mult_ab / mult_abt / mult_vec -> from_handle -> release_handle, all nopython).  Results against the
+    numba kernel in object mode: rowptrs bit-exact, colinds after the canonical sort, values rtol 1e-10."""
+    ok(run_py("""
+import numpy as np, scipy.sparse as sps
+from numba import njit
+import csr, csr.kernel
+from csr import CSR
+from csr.kernels import use_kernel
+assert csr.kernel.name == 'csr.kernels.cuda'
+rng = np.random.default_rng(9)
+def rand(nr, nc, dens):
+    m = sps.random(nr, nc, dens, format='csr', random_state=rng, data_rvs=lambda n: rng.uniform(0.5, 5.0, n))
+    return CSR.from_scipy(m)
+A, B, Bt = rand(250, 180, 0.06), rand(180, 140, 0.07), rand(160, 180, 0.05)
+x = rng.standard_normal(180)
+
+@njit
+def products(a, b, bt, x):
+    return a.multiply(b, False), a.multiply(bt, True), a.mult_vec(x)
+
+ab, abt, y = products(A, B, Bt, x)
+def canon(m):
+    rows = np.repeat(np.arange(m.nrows), np.diff(m.rowptrs))
+    o = np.lexsort((m.colinds, rows))
+    return m.rowptrs, m.colinds[o], m.values[o]
+with use_kernel('numba'):
+    r_ab, r_abt, r_y = A.multiply(B), A.multiply(Bt, transpose=True), A.mult_vec(x)
+for got, ref in ((ab, r_ab), (abt, r_abt)):
+    assert type(got) is CSR
+    rp, ci, vs = canon(ref)
+    assert got.rowptrs.dtype == rp.dtype and np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
+    assert np.allclose(got.values, vs, rtol=1e-10, atol=0)
+assert np.allclose(y, r_y, rtol=1e-10, atol=1e-12)
+from csr_b200 import _native
+assert _native.launch_count() > 0          # the products above ran on the GPU
+""", env_extra={"CSR_KERNEL": "cuda"}))

@@ -74,3 +74,38 @@ def test_product_and_export_from_nopython(kernel):
     want = orc.canonical(orc.mult_abt(A, A))          # and against the oracle, not only CUDA against CUDA
     assert np.array_equal(rp, want.rowptrs) and np.array_equal(ci, want.colinds)
     assert np.allclose(vs, want.values, rtol=1e-10, atol=0.0)
+
+
+@njit
+def _roundtrip(nrows, ncols, nnz, rp, ci, vs, x):
+    "to_handle -> mult_vec -> from_handle -> release_handle, all from nopython code."
+    h = cn.create(nrows, ncols, nnz, rp, ci, vs)
+    y = cn.mult_vec(h, x)
+    out = cn.export_arrays(h)
+    cn.release_handle(h)
+    return y, out
+
+
+@njit
+def _roundtrip_structure(nrows, ncols, nnz, rp, ci, x):
+    h = cn.create_structure(nrows, ncols, nnz, rp, ci)
+    y = cn.mult_vec(h, x)
+    cn.release_handle(h)
+    return y
+
+
+@pytest.mark.parametrize("dtype,rp64", [("f8", False), ("f4", True)])
+def test_handle_lifecycle_from_nopython(kernel, dtype, rp64):
+    A = synth.powerlaw_csr(3000, 2000, 90000, seed=39, dtype=dtype, alpha=0.9)
+    rp = A.rowptrs.astype(np.int64 if rp64 else np.int32)
+    x = synth.dense_vector(A.ncols, 5, "f8")
+    y, (nr, nc, nnz, rpo, cio, vso) = _roundtrip(A.nrows, A.ncols, A.nnz, rp, A.colinds, A.values, x)
+    assert (nr, nc, nnz) == (A.nrows, A.ncols, A.nnz)
+    assert np.array_equal(rpo, A.rowptrs) and np.array_equal(cio, A.colinds) and np.array_equal(vso, A.values.astype(np.float64))
+    want = orc.mult_vec(A, x)
+    tol = 1e-5 if dtype == "f4" else 1e-10
+    assert np.allclose(y, want, rtol=tol, atol=tol * np.abs(want).max())
+    ys = _roundtrip_structure(A.nrows, A.ncols, A.nnz, rp, A.colinds, x)
+    S = orc.Mat(A.nrows, A.ncols, A.nnz, A.rowptrs, A.colinds, None)
+    ws = orc.mult_vec(S, x)
+    assert np.allclose(ys, ws, rtol=1e-10, atol=1e-10 * np.abs(ws).max())

@@ -169,7 +169,8 @@ def test_empty_rows_and_columns(slab):
 
 
 def test_auto_mode_picks_by_cost_model(kernel):
-    "auto: the stream kernel only when the matrix is large and x (re-read per SM) is smaller than the entry stream"
+    """auto: the slab kernel only when the matrix is large and x (re-read per SM) costs at most 1.6 x the entry stream,
+    and only from the SECOND mult_vec of a handle on (one-shot handles, csr/csr.py:582, never build a plan)"""
     kernel.set_option("stream_min_nnz", 100000)
     try:
         A = synth.powerlaw_csr(20000, 1000, 400000, seed=81, dtype="f4", alpha=0.8)      # 148*4 KB << 3.2 MB
@@ -178,9 +179,12 @@ def test_auto_mode_picks_by_cost_model(kernel):
             x = synth.dense_vector(M.ncols, 83, "f4")
             h = kernel.to_handle(M)
             y = kernel.mult_vec(h, x)
+            assert kernel.spmv_plan_info(h, 4)["kernel"] == "tile"          # first call: no plan yet
+            y2 = kernel.mult_vec(h, x)
             info = kernel.spmv_plan_info(h, 4)
             kernel.release_handle(h)
             assert info["kernel"] == want, info
             assert_values_close(y, orc.mult_vec(M, x), 1e-5, _scale(M, x))
+            assert_values_close(y2, orc.mult_vec(M, x), 1e-5, _scale(M, x))
     finally:
         kernel.set_option("stream_min_nnz", 4000000)
