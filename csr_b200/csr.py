@@ -252,21 +252,20 @@ class CSR:
 
     @contextmanager
     def _row_blocks(self, K):
-        """Handles of the row blocks of at most ``K.max_nnz`` entries: the whole matrix when it fits
-        (the common case), else device-side slices of ONE upload."""
-        with self._on_device(K) as h:
-            cuts = _row_cuts(self.rowptrs, K.max_nnz)
-            if len(cuts) == 2:
+        """Handles of the row blocks of at most ``K.max_nnz`` entries: the whole matrix when it fits (the
+        common case); else one upload per block (csr/csr.py:558-566,581-590: no handle may exceed ``max_nnz``)."""
+        if self.nnz <= K.max_nnz:
+            with self._on_device(K) as h:
                 yield [h]
-                return
-            blocks = []
-            try:
-                for b, e in zip(cuts[:-1], cuts[1:]):
-                    blocks.append(K.subset_rows(h, b, e))
-                yield blocks
-            finally:
-                for blk in blocks:
-                    K.release_handle(blk)
+            return
+        blocks = []
+        try:
+            for shard in self._shard_rows(K.max_nnz):
+                blocks.append(K.to_handle(shard))
+            yield blocks
+        finally:
+            for blk in blocks:
+                K.release_handle(blk)
 
     # ------------------------------------------------------------ the kernel's callers
     def multiply(self, other, transpose=False):

@@ -382,20 +382,20 @@ def test_keep_resident_handle_cache(kernel):
     A = synth.powerlaw_csr(500, 400, 6000, seed=91, dtype="f8").keep_resident()
     x = synth.dense_vector(400, 92, "f8")
     y1 = A.mult_vec(x)
-    h1 = csr_mod._cache.entries[id(A)][1]
+    h1 = csr_mod._resident._live[id(A)][1]
     y2 = A.mult_vec(x)
-    assert csr_mod._cache.entries[id(A)][1] is h1 and h1.H
+    assert csr_mod._resident._live[id(A)][1] is h1 and h1.H
     assert np.array_equal(y1, y2)
     assert_values_close(y1, orc.mult_vec(A, x), 1e-10, _mv_scale(A, x))
     A.values = A.values * 2.0            # re-assigned values invalidate the cached handle
-    assert not h1.H and id(A) not in csr_mod._cache.entries
+    assert not h1.H and id(A) not in csr_mod._resident._live
     assert_values_close(A.mult_vec(x), 2.0 * y1, 1e-12, _mv_scale(A, x))
-    h2 = csr_mod._cache.entries[id(A)][1]
+    h2 = csr_mod._resident._live[id(A)][1]
     key = id(A)
     del A
     import gc
     gc.collect()
-    assert key not in csr_mod._cache.entries and not h2.H
+    assert key not in csr_mod._resident._live and not h2.H
 
 
 def test_released_handle_is_rejected(kernel):
