@@ -1050,6 +1050,7 @@ def run_reference(args):
     t1 = time_best(lambda: arm.mult_vec(Ar, x), 2)
     sample = (f"the full block ({A.nnz} nnz) per step, {arm.cores} threads over "
               f"{'CSR._shard_rows blocks (csr/csr.py:599-621)' if arm.ref else 'row blocks'}")
+    spgemm = reference_spgemm(args, arm) if args.spgemm_scale > 0 else None
     emit({
         "impl": "reference", "metric": "spmv_hbm_gbs", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4), "higher_is_better": True,
@@ -1058,7 +1059,30 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": arm.cores, "kind": arm.kind, "impl": arm.name,
                          "sample": sample, "serial_value": round(b / t1 / 1e9, 3), "cpu": cpu_model()},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        **({"spgemm": spgemm} if spgemm else {}),
     })
+
+
+def reference_spgemm(args, arm):
+    "configs[2] on the CPU arm: mult_ab(S, M^T) for the same every-k-th-row sample of A that cpu_baseline uses."
+    from csr_b200 import synth
+    from csr_b200.dist import spgemm_row_weights
+    from oracle import oracle as orc
+    R = synth.cfg3_ratings(args.spgemm_scale)
+    Mo = orc.transpose(orc.as_mat(R))                     # M = ratings^T (items x users)
+    user_len = np.bincount(Mo.colinds, minlength=Mo.ncols).astype(np.int64)
+    _, prod_row = spgemm_row_weights(Mo, user_len, Mo.nrows)
+    stride = max(int(np.ceil(prod_row.sum() / 4e8)), 1)
+    pick = np.arange(0, Mo.nrows, stride)
+    S = take_rows(Mo, pick)
+    Bt = arm.transpose(arm.matrix(Mo))
+    tcpu, zs = arm.mult_ab_blocks(arm.matrix(S), Bt)
+    ps = int(prod_row[pick].sum())
+    return {"metric": "spgemm_abt_out_nnz_per_s", "value": round(zs / tcpu, 1), "unit": "nnz/s", "cores": arm.cores,
+            "kind": arm.kind, "products_per_s": round(ps / tcpu, 1),
+            "workload": f"BASELINE configs[2] x{args.spgemm_scale}: M={Mo.nrows}x{Mo.ncols}, {Mo.nnz} nnz f64, mult_abt(M,M)",
+            "sample": f"every {stride}th row of A: {len(pick)} of {Mo.nrows} rows ({zs} out-nnz, {ps} products), one run on "
+                      f"{arm.cores} threads over CSR._shard_rows blocks, transpose excluded"}
 
 
 def main():
