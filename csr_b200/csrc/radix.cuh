@@ -71,8 +71,10 @@ template <typename VT> struct RadixSmem {
 // Stable rank + scatter of one tile.  The tile is put in its sorted order in shared memory
 // (digit-major, stable) and written out with consecutive threads on consecutive addresses:
 // every digit's run of the tile is one contiguous burst in HBM instead of 4-8 byte pieces.
+// (9-bit digits with a float64 payload need 74 registers: at 4 CTAs per SM -- 64 registers -- the kernel spilled
+// 92 bytes per thread; 3 CTAs per SM are enough to cover its latency)
 template <typename VT, int DB>
-__global__ void __launch_bounds__(RS_BLOCK, 4)
+__global__ void __launch_bounds__(RS_BLOCK, (DB == 9 && sizeof(VT) == 8) ? 3 : 4)
 k_radix_scatter(const int32_t *__restrict__ keys_in, const int32_t *__restrict__ rows_in, const VT *__restrict__ vals_in,
                 int32_t *__restrict__ keys_out, int32_t *__restrict__ rows_out, VT *__restrict__ vals_out, int64_t n,
                 int shift, const int64_t *__restrict__ tile_off, int64_t ntiles)

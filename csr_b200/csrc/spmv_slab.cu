@@ -372,7 +372,7 @@ k_sl_fill(int64_t NI, const int64_t *__restrict__ itembase, int64_t ncells, cons
 }
 
 __global__ void k_sl_bins(const int64_t *__restrict__ itembase, const int64_t *__restrict__ itemoff, int B, int nslab,
-                          int64_t *__restrict__ binbase, uint32_t *__restrict__ binlen)
+                          int64_t *__restrict__ binbase, uint32_t *__restrict__ binlen, int ring, int *__restrict__ too_long)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B)
@@ -380,6 +380,8 @@ __global__ void k_sl_bins(const int64_t *__restrict__ itembase, const int64_t *_
     const int64_t o0 = itemoff[itembase[(int64_t)b * nslab]], o1 = itemoff[itembase[(int64_t)(b + 1) * nslab]];
     binbase[b] = o0;
     binlen[b] = (uint32_t)(o1 - o0);
+    if (o1 - o0 + ring >= ((int64_t)1 << 31))
+        *too_long = 1;   // positions inside a warp's stream are 32-bit
 }
 
 static int sl_bits(int64_t n)
@@ -539,11 +541,15 @@ static int stream_build_typed(csrk_matrix *h, StreamPlan *P, cudaStream_t s)
     CSRK_LAUNCH((k_sl_fill<VT>), (unsigned)div_up(NI * 32, 256), 256, 0, s, NI, itembase.as<int64_t>(), ncells,
                 bnd.as<int32_t>(), slen.as<int32_t>(), srid.as<int32_t>(), rs.as<int32_t>(), spacked.as<int32_t>(),
                 HASV ? svals.as<VT>() : nullptr, itemoff.as<int64_t>(), cellsub.as<int32_t>(), P->stream, P->P, P->S);
+    DevBuf toolong;
+    CSRK_TRY(toolong.alloc_zero(sizeof(int), s));
     CSRK_LAUNCH(k_sl_bins, (unsigned)div_up(B, 256), 256, 0, s, itembase.as<int64_t>(), itemoff.as<int64_t>(), B, P->nslab,
-                P->binbase, P->binlen);
+                P->binbase, P->binlen, P->ring, toolong.as<int>());
+    int too_long = 0;
+    CSRK_CUDA(cudaMemcpyAsync(&too_long, toolong.as<int>(), sizeof(int), cudaMemcpyDeviceToHost, s));
     CSRK_CUDA(cudaMemcpyAsync(&P->n_split, splitcnt.as<int>(), sizeof(int), cudaMemcpyDeviceToHost, s));
     CSRK_CUDA(cudaStreamSynchronize(s));
-    if (total / B + P->ring >= ((int64_t)1 << 31))
+    if (too_long)
     {
         set_error("slab plan: a warp's stream of %lld bytes needs 64-bit positions", (long long)(total / B));
         return CSRK_EOVERFLOW;   // positions inside a bin's stream are 32-bit
