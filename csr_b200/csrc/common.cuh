@@ -140,6 +140,7 @@ struct Options {
     std::atomic<int64_t> radix_bits{0};                 // digit width of the stable sort: 0 = pick (9 when it saves a pass), 8, 9
     std::atomic<int64_t> spmv_zero_copy_y{1};           // csrk_spmv: store rows straight into pinned host y
     std::atomic<int64_t> fix_threads{1024};             // threads per CTA of the fixed-point SpGEMM kernel (512 | 768 | 1024)
+    std::atomic<int64_t> sym_bytes{1};                  // SpGEMM symbolic pass of heavy rows: byte marks with plain stores when the columns fit
     std::atomic<int64_t> spgemm_fixed{1};               // SpGEMM heavy rows: fixed-point atomics when the value range allows
     std::atomic<int64_t> own_chunk_prod{0};             // SpGEMM heavy-row chunking: 0 auto, > 0 products per chunk, < 0 off
     std::atomic<int64_t> own_nw{16};                    // warps (column ranges) per CTA in the owner-computes SpGEMM

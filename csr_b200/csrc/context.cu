@@ -390,6 +390,8 @@ int csrk_set_option(const char *name, int64_t value)
     } else if (!strcmp(name, "stream_ring_chunks")) {
         CSRK_ARG(value == 2 || value == 4, "stream_ring_chunks must be 2 or 4");
         options().stream_ring_chunks = value;
+    } else if (!strcmp(name, "sym_bytes")) {
+        options().sym_bytes = value ? 1 : 0;
     } else if (!strcmp(name, "stream_xbufs")) {
         CSRK_ARG(value == 2 || value == 3, "stream_xbufs must be 2 or 3");
         options().stream_xbufs = value;

@@ -209,21 +209,52 @@ __global__ void __launch_bounds__(THREADS) k_sym_cta(MatView A, MatView B, const
 // scratch; either way it is restored to zero while it is counted.  When `keep` is
 // given, the row's bitmap is also stored there (slot = position in the bin) so the
 // numeric phase does not have to rebuild it: keep_slot[row] = slot.
-template <bool SMEM_BM, int THREADS>
+// BYTES: the marks are one BYTE per column in shared memory, set with plain stores (idempotent: no atomics;
+// stores of several lanes into one 32-bit word merge in the same wavefront, where atomicOr on the hot words of
+// popular columns serialises), and packed into bitmap words while they are counted.
+template <bool SMEM_BM, int THREADS, bool BYTES = false>
 __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin,
                                                         int32_t *__restrict__ row_nnz, unsigned *__restrict__ gbm,
                                                         int n_words, int *__restrict__ work_counter,
                                                         unsigned *__restrict__ keep, int32_t *__restrict__ keep_slot,
                                                         const int *__restrict__ item_off)
 {
-    extern __shared__ unsigned s_bm[];
+    extern __shared__ __align__(16) unsigned s_bm[];
     __shared__ int s_idx, s_item, s_count;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    static_assert(!BYTES || SMEM_BM, "the byte map lives in shared memory");
     unsigned *bm = SMEM_BM ? s_bm : gbm + (size_t)blockIdx.x * n_words;
+    unsigned char *by = reinterpret_cast<unsigned char *>(s_bm);   // BYTES: 32 bytes per bitmap word
     if (SMEM_BM) {
-        for (int i = tid; i < n_words; i += THREADS)
+        for (int i = tid; i < n_words * (BYTES ? 8 : 1); i += THREADS)
             s_bm[i] = 0;
     }
+    // the 32 marks of bitmap word i -> the word, and the marks back to zero
+    auto take_word = [&](int i) -> unsigned {
+        if constexpr (BYTES) {
+            uint4 *p = reinterpret_cast<uint4 *>(by + 32 * (size_t)i);
+            const uint4 q0 = p[0], q1 = p[1];
+            const unsigned w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            unsigned bits = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                bits |= ((w[j] & 1u) | ((w[j] >> 7) & 2u) | ((w[j] >> 14) & 4u) | ((w[j] >> 21) & 8u)) << (4 * j);
+            if (bits) {
+                p[0] = make_uint4(0u, 0u, 0u, 0u);
+                p[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            return bits;
+        } else {
+            const unsigned bits = SMEM_BM ? bm[i] : __ldcg(&bm[i]);
+            if (bits) {
+                if (SMEM_BM)
+                    bm[i] = 0;
+                else
+                    __stcg(&bm[i], 0u);
+            }
+            return bits;
+        }
+    };
     while (true) {
         __syncthreads();
         if (tid == 0) {
@@ -269,7 +300,10 @@ __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, co
             const int64_t bs = ld_rp(B.rp, B.rp64, j), be = ld_rp(B.rp, B.rp64, (int64_t)j + 1);
             for (int64_t kk = bs + lane; kk < be; kk += 32) {
                 const int32_t k = B.ci[kk];
-                atomicOr(&bm[k >> 5], 1u << (k & 31));
+                if constexpr (BYTES)
+                    by[k] = 1;
+                else
+                    atomicOr(&bm[k >> 5], 1u << (k & 31));
             }
         }
         __syncthreads();
@@ -278,28 +312,17 @@ __global__ void __launch_bounds__(THREADS) k_sym_bitmap(MatView A, MatView B, co
         if (nch > 1) {
             // OR this chunk's columns into the row's (zero-initialised) kept bitmap; k_sym_finish counts it
             for (int i = tid; i < n_words; i += THREADS) {
-                const unsigned bits = SMEM_BM ? bm[i] : __ldcg(&bm[i]);
-                if (bits) {
+                const unsigned bits = take_word(i);
+                if (bits)
                     atomicOr(&dst[i], bits);
-                    if (SMEM_BM)
-                        bm[i] = 0;
-                    else
-                        __stcg(&bm[i], 0u);
-                }
             }
             continue;
         }
         for (int i = tid; i < n_words; i += THREADS) {
-            const unsigned bits = SMEM_BM ? bm[i] : __ldcg(&bm[i]);
+            const unsigned bits = take_word(i);
             if (dst)
                 dst[i] = bits;
-            if (bits) {
-                count += __popc(bits);
-                if (SMEM_BM)
-                    bm[i] = 0;
-                else
-                    __stcg(&bm[i], 0u);
-            }
+            count += __popc(bits);
         }
         count = warp_sum(count);
         if (lane == 0 && count)
@@ -1394,7 +1417,14 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
             sio = s_item_off.as<int>();
         }
         const int64_t max_items = (int64_t)cnt[5] + (sio ? (int64_t)sms * 8 + 1 : 0);
-        if (bm_bytes + 1024 <= smem_max - 8 * 1024) {
+        if (options().sym_bytes.load() && bm_bytes * 8 <= 100 * 1024) {
+            // one byte per column, plain stores (up to 102 400 columns: two CTAs per SM; four below 51 200)
+            auto k = k_sym_bitmap<true, DENSE_THREADS, true>;
+            CSRK_TRY(optin_smem(k, bm_bytes * 8));
+            const int grid = (int)std::min(max_items, (int64_t)sms * (bm_bytes * 8 > 50 * 1024 ? 2 : 4));
+            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes * 8, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
+                        (unsigned *)nullptr, n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>(), sio);
+        } else if (bm_bytes + 1024 <= smem_max - 8 * 1024) {
             auto k = k_sym_bitmap<true, DENSE_THREADS>;
             CSRK_TRY(optin_smem(k, bm_bytes));
             const int grid = (int)std::min(max_items, (int64_t)sms * (bm_bytes > 100 * 1024 ? 1 : 2));
