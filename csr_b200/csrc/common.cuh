@@ -143,6 +143,9 @@ struct Options {
     std::atomic<int64_t> sym_bytes{1};                  // SpGEMM symbolic pass of heavy rows: byte marks with plain stores when the columns fit
     std::atomic<int64_t> spgemm_fixed{1};               // SpGEMM heavy rows: fixed-point atomics when the value range allows
     std::atomic<int64_t> own_chunk_prod{0};             // SpGEMM heavy-row chunking: 0 auto, > 0 products per chunk, < 0 off
+    std::atomic<int64_t> spgemm_esc{1};                 // SpGEMM expand/sort/compress path: 0 off, 1 for wide results, 2 always (tests)
+    std::atomic<int64_t> esc_target{1536};              // products per pseudo-row (row x column range) of that path
+    std::atomic<int64_t> esc_budget{0};                 // > 0: cap in bytes on its expansion (else: half of the free memory)
     std::atomic<int64_t> own_nw{16};                    // warps (column ranges) per CTA in the owner-computes SpGEMM
 };
 Options &options();

@@ -407,6 +407,15 @@ int csrk_set_option(const char *name, int64_t value)
         options().spgemm_fixed = value ? 1 : 0;
     } else if (!strcmp(name, "own_chunk_prod")) {
         options().own_chunk_prod = value;
+    } else if (!strcmp(name, "spgemm_esc")) {
+        CSRK_ARG(value >= 0 && value <= 2, "spgemm_esc must be 0 (off), 1 (wide results) or 2 (always)");
+        options().spgemm_esc = value;
+    } else if (!strcmp(name, "esc_target")) {
+        CSRK_ARG(value >= 16 && value <= 4096, "esc_target must be in 16..4096");
+        options().esc_target = value;
+    } else if (!strcmp(name, "esc_budget")) {
+        CSRK_ARG(value >= 0, "esc_budget is a byte count (0 = what the device has free)");
+        options().esc_budget = value;
     } else if (!strcmp(name, "own_nw")) {
         CSRK_ARG(value == 8 || value == 16, "own_nw must be 8 or 16");
         options().own_nw = value;

@@ -1336,6 +1336,18 @@ static int make_empty_result(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cu
     return CSRK_OK;
 }
 
+}  // namespace csrk
+#include "spgemm_esc.cuh"
+namespace csrk {
+
+__global__ void __launch_bounds__(256) k_esc_zero_rows(const int32_t *__restrict__ rows, int n, const int *__restrict__ bad,
+                                                        int32_t *__restrict__ row_nnz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !bad[i])
+        row_nnz[rows[i]] = 0;
+}
+
 int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
 {
     *c = nullptr;
@@ -1379,6 +1391,19 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     DevBuf counter;
     CSRK_TRY(counter.alloc_zero(sizeof(int) * 2, s));
     const int32_t *L = list.as<int32_t>();
+    // Wide results (more column windows than the dense kernels take): rows above the small hash bins go
+    // through the expand / sort / compress path (spgemm_esc.cuh), which also does their numeric work; rows it
+    // hands back (skewed beyond a pseudo-row's capacity) and everything else follow the bins below.
+    EscState esc;
+    const int64_t esc_opt = options().spgemm_esc.load();
+    if (esc_opt == 2 || (esc_opt == 1 && div_up((int64_t)n, DENSE_WIN) > DENSE_MAX_PASSES)) {
+        CSRK_TRY(esc_symbolic(A, B, L + off[3], cnt[3] + cnt[4] + cnt[5], prod.as<int64_t>(), both_f32, row_nnz.as<int32_t>(),
+                              esc, s));
+        if (esc.active)
+            cnt[3] = cnt[4] = 0;
+    }
+    const int32_t *L5 = esc.active ? esc.old_list.as<int32_t>() : L + off[5];
+    const int cnt5 = esc.active ? esc.n_old : cnt[5];
     if (cnt[1])
         CSRK_LAUNCH((k_sym_warp<SYM_WARP_SLOTS>), (unsigned)div_up(cnt[1], 8), 256, 0, s, A, B, L + off[1], cnt[1],
                     row_nnz.as<int32_t>());
@@ -1396,49 +1421,49 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
         CSRK_LAUNCH(k, (unsigned)cnt[4], 256, SYM_C3 * 4, s, A, B, L + off[4], row_nnz.as<int32_t>());
     }
     DevBuf gbm, keep, keep_slot;
-    if (cnt[5]) {
+    if (cnt5) {
         const size_t bm_bytes = (size_t)n_words * 4;
-        if (bm_bytes * (size_t)cnt[5] <= KEEP_BITMAP_BUDGET) {
-            CSRK_TRY(keep.alloc(bm_bytes * (size_t)cnt[5], s));
+        if (bm_bytes * (size_t)cnt5 <= KEEP_BITMAP_BUDGET) {
+            CSRK_TRY(keep.alloc(bm_bytes * (size_t)cnt5, s));
             CSRK_TRY(keep_slot.alloc(sizeof(int32_t) * (size_t)m, s));
         }
         // chunked symbolic rows OR into their kept bitmap, so chunking needs the kept bitmaps (zeroed)
         DevBuf s_nchunk, s_nsplit, s_last, s_item_off;
         const int *sio = nullptr;
         if (chunking && keep.p) {
-            CSRK_TRY(s_nchunk.alloc(sizeof(int) * (size_t)cnt[5], s));
-            CSRK_TRY(s_nsplit.alloc(sizeof(int) * (size_t)cnt[5], s));
+            CSRK_TRY(s_nchunk.alloc(sizeof(int) * (size_t)cnt5, s));
+            CSRK_TRY(s_nsplit.alloc(sizeof(int) * (size_t)cnt5, s));
             CSRK_TRY(s_last.alloc_zero(sizeof(int), s));
-            CSRK_TRY(s_item_off.alloc(sizeof(int) * ((size_t)cnt[5] + 1), s));
-            CSRK_LAUNCH(k_own_items, (unsigned)div_up(cnt[5], 256), 256, 0, s, A, L + off[5], cnt[5], prod.as<int64_t>(),
+            CSRK_TRY(s_item_off.alloc(sizeof(int) * ((size_t)cnt5 + 1), s));
+            CSRK_LAUNCH(k_own_items, (unsigned)div_up(cnt5, 256), 256, 0, s, A, L5, cnt5, prod.as<int64_t>(),
                         chunk_prod, s_nchunk.as<int>(), s_nsplit.as<int>(), s_last.as<int>());
-            CSRK_TRY((exclusive_scan<int>(ArrayLoader<int>{s_nchunk.as<int>()}, (int64_t)cnt[5], s_item_off.as<int>(), s)));
-            CSRK_CUDA(cudaMemsetAsync(keep.p, 0, bm_bytes * (size_t)cnt[5], s));
+            CSRK_TRY((exclusive_scan<int>(ArrayLoader<int>{s_nchunk.as<int>()}, (int64_t)cnt5, s_item_off.as<int>(), s)));
+            CSRK_CUDA(cudaMemsetAsync(keep.p, 0, bm_bytes * (size_t)cnt5, s));
             sio = s_item_off.as<int>();
         }
-        const int64_t max_items = (int64_t)cnt[5] + (sio ? (int64_t)sms * 8 + 1 : 0);
+        const int64_t max_items = (int64_t)cnt5 + (sio ? (int64_t)sms * 8 + 1 : 0);
         if (options().sym_bytes.load() && bm_bytes * 8 <= 100 * 1024) {
             // one byte per column, plain stores (up to 102 400 columns: two CTAs per SM; four below 51 200)
             auto k = k_sym_bitmap<true, DENSE_THREADS, true>;
             CSRK_TRY(optin_smem(k, bm_bytes * 8));
             const int grid = (int)std::min(max_items, (int64_t)sms * (bm_bytes * 8 > 50 * 1024 ? 2 : 4));
-            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes * 8, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
+            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes * 8, s, A, B, L5, cnt5, row_nnz.as<int32_t>(),
                         (unsigned *)nullptr, n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>(), sio);
         } else if (bm_bytes + 1024 <= smem_max - 8 * 1024) {
             auto k = k_sym_bitmap<true, DENSE_THREADS>;
             CSRK_TRY(optin_smem(k, bm_bytes));
             const int grid = (int)std::min(max_items, (int64_t)sms * (bm_bytes > 100 * 1024 ? 1 : 2));
-            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
+            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, bm_bytes, s, A, B, L5, cnt5, row_nnz.as<int32_t>(),
                         (unsigned *)nullptr, n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>(), sio);
         } else {
             auto k = k_sym_bitmap<false, DENSE_THREADS>;
             const int grid = (int)std::min(max_items, (int64_t)sms * 2);
             CSRK_TRY(gbm.alloc_zero(bm_bytes * (size_t)grid, s));
-            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, L + off[5], cnt[5], row_nnz.as<int32_t>(),
+            CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, L5, cnt5, row_nnz.as<int32_t>(),
                         gbm.as<unsigned>(), n_words, counter.as<int>(), keep.as<unsigned>(), keep_slot.as<int32_t>(), sio);
         }
         if (sio)
-            CSRK_LAUNCH(k_sym_finish, (unsigned)cnt[5], 128, 0, s, L + off[5], sio, n_words, keep.as<unsigned>(),
+            CSRK_LAUNCH(k_sym_finish, (unsigned)cnt5, 128, 0, s, L5, sio, n_words, keep.as<unsigned>(),
                         row_nnz.as<int32_t>(), keep_slot.as<int32_t>());
     }
 
@@ -1453,6 +1478,9 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     BinSpec nspec{{0, NUM_WARP_SLOTS / 2, NUM_C1 / 2, NUM_C2 / 2, NUM_C3 / 2, INT64_MAX}};
     int ncnt[NBINS], noff[NBINS + 1];
     DevBuf nlist;
+    if (esc.active)   // their values exist already (esc_emit copies them): keep them out of the numeric bins
+        CSRK_LAUNCH(k_esc_zero_rows, (unsigned)div_up(esc.n_rows, 256), 256, 0, s, esc.rows, esc.n_rows, esc.bad.as<int>(),
+                    row_nnz.as<int32_t>());
     CSRK_TRY(bin_rows(row_nnz.as<int32_t>(), (int64_t)m, nspec, ncnt, noff, nlist, s));
     gbm.reset();
 
@@ -1503,6 +1531,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     const int64_t *crp = rp64.as<int64_t>();
     double *cvs = (double *)out->vs;
     auto numeric = [&]() -> int {
+        CSRK_TRY(esc_emit(esc, crp, out->ci, cvs, s));
         if (ncnt[1])
             CSRK_LAUNCH((k_num_warp<NUM_WARP_SLOTS>), (unsigned)div_up(ncnt[1], 8), 256, 0, s, A, B, NL + noff[1], ncnt[1],
                         crp, out->ci, cvs, both_f32);

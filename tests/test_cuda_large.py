@@ -203,6 +203,93 @@ def test_spgemm_wide_global_scratch(kernel):
     _check_mm(kernel, A, B, False, 1e-10)
 
 
+def _with_options(kernel, opts, fn):
+    defaults = {"spgemm_esc": 1, "esc_target": 1536, "esc_budget": 0}
+    for k, v in opts.items():
+        kernel.set_option(k, v)
+    try:
+        return fn()
+    finally:
+        for k in opts:
+            kernel.set_option(k, defaults[k])
+
+
+def test_spgemm_wide_old_global_scratch(kernel):
+    "the same product with the expand/sort/compress path switched off: per-CTA global scratch accumulators"
+    A = synth.powerlaw_csr(300, 2000, 40000, seed=53, dtype="f8", alpha=1.2)
+    B = synth.powerlaw_csr(2000, 2_000_000, 300000, seed=54, dtype="f8", alpha=0.5)
+    _with_options(kernel, {"spgemm_esc": 0}, lambda: _check_mm(kernel, A, B, False, 1e-10))
+
+
+@pytest.mark.parametrize("target", [16, 64, 1536, 4096])
+@pytest.mark.parametrize("tr", [False, True])
+def test_spgemm_esc_forced(kernel, target, tr):
+    """Expand/sort/compress path forced on a product with every row size (spgemm_esc.cuh): pseudo-rows of
+    `target` products -> all four reduce kernels, rows cut into up to thousands of column ranges."""
+    A = synth.powerlaw_csr(1500, 4000, 30000, seed=51, dtype="f8", alpha=1.5)
+    B = synth.powerlaw_csr(4000, 30000, 150000, seed=52, dtype="f8", alpha=1.2)
+    if tr:
+        B = B.transpose()
+    got, st = _with_options(kernel, {"spgemm_esc": 2, "esc_target": target}, lambda: _check_mm(kernel, A, B, tr, 1e-10))
+    assert np.diff(got.rowptrs).max() > 8192
+
+
+def test_spgemm_esc_f32_products(kernel):
+    "f4 x f4 products are rounded to float32 before they are summed (numba's promotion), on this path too"
+    A = synth.powerlaw_csr(800, 3000, 40000, seed=61, dtype="f4", alpha=1.3)
+    B = synth.powerlaw_csr(3000, 150_000, 200000, seed=62, dtype="f4", alpha=1.0)
+    _with_options(kernel, {"spgemm_esc": 2}, lambda: _check_mm(kernel, A, B, False, 1e-5))
+
+
+def test_spgemm_esc_hands_back_skewed_rows(kernel):
+    """All of B's columns sit in the first 0.05 % of a 2M-column range: the uniform column ranges put a whole
+    row into one pseudo-row; rows beyond its capacity go back to the old kernels, the others stay."""
+    rng = np.random.default_rng(63)
+    A = synth.powerlaw_csr(400, 2000, 40000, seed=64, dtype="f8", alpha=1.2)
+    Bn = synth.powerlaw_csr(2000, 1000, 300000, seed=65, dtype="f8", alpha=0.5)
+    B = CSR(2000, 2_000_000, Bn.nnz, Bn.rowptrs, Bn.colinds, Bn.values)
+    got, st = _check_mm(kernel, A, B, False, 1e-10)
+    lens = np.diff(B.rowptrs)
+    P = np.add.reduceat(np.concatenate([lens[A.colinds], [0]]), np.minimum(A.rowptrs[:-1], A.nnz))
+    P[np.diff(A.rowptrs) == 0] = 0
+    assert (P > 8192).any() and ((P > 1024) & (P <= 8192)).any()
+
+
+def test_spgemm_esc_declines_over_budget(kernel):
+    A = synth.powerlaw_csr(300, 2000, 40000, seed=53, dtype="f8", alpha=1.2)
+    B = synth.powerlaw_csr(2000, 2_000_000, 300000, seed=54, dtype="f8", alpha=0.5)
+    _with_options(kernel, {"esc_budget": 4096}, lambda: _check_mm(kernel, A, B, False, 1e-10))
+
+
+def test_spgemm_esc_columns_pile_up(kernel):
+    """B uses 40 distinct columns of 300 000: every pseudo-row has buckets of hundreds of equal columns, the
+    bucket-sort kernel flags it and the hash kernel takes over (k_esc_reduce)."""
+    rng = np.random.default_rng(68)
+    A = synth.powerlaw_csr(300, 800, 30000, seed=69, dtype="f8", alpha=1.0)
+    hot = np.sort(rng.choice(300_000, 40, replace=False)).astype(np.int32)
+    lens = rng.integers(1, 30, 800)
+    rp = np.zeros(801, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    cols = np.concatenate([np.sort(rng.choice(hot, int(l), replace=False)) for l in lens]).astype(np.int32)
+    B = CSR(800, 300_000, int(rp[-1]), rp, cols, rng.normal(size=int(rp[-1])))
+    for target in (64, 1536):
+        _with_options(kernel, {"spgemm_esc": 2, "esc_target": target}, lambda: _check_mm(kernel, A, B, False, 1e-10))
+
+
+def test_spgemm_esc_unsorted_duplicate_columns(kernel):
+    "B rows with unsorted and repeated columns (legal CSR for the reference: multiply.py:60-129 has no order assumption)"
+    rng = np.random.default_rng(66)
+    A = synth.powerlaw_csr(200, 500, 20000, seed=67, dtype="f8", alpha=1.0)
+    lens = rng.integers(0, 120, 500)
+    rp = np.zeros(501, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    cols = rng.integers(0, 300_000, int(rp[-1])).astype(np.int32)
+    idx = np.arange(0, len(cols) - 1, 7)
+    cols[idx] = cols[idx + 1]      # repeated columns, mostly inside one row
+    B = CSR(500, 300_000, int(rp[-1]), rp, cols, rng.normal(size=int(rp[-1])))
+    _with_options(kernel, {"spgemm_esc": 2, "esc_target": 256}, lambda: _check_mm(kernel, A, B, False, 1e-10))
+
+
 @pytest.mark.parametrize("dtype", ["f8", "f4"])
 def test_item_item_abt(kernel, dtype):
     "configs[2] shape, scaled: M = ratings^T, M M^T"
