@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(256) k_esc_reduce_warp(const int32_t *__restri
 // A pseudo-row with a bucket of more than ESC_BUCKET_MAX products (one column hit very often, clustered
 // columns) is left untouched and flagged: k_esc_reduce below takes it.
 constexpr int ESC_BUCKET_MAX = 32;
+constexpr int ESC_BPP = 2;   // buckets per product of capacity
 
 template <int THREADS, int PER, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *__restrict__ plist, int nbin,
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *
                                                                  int32_t *__restrict__ pnnz, int *__restrict__ fail,
                                                                  int *__restrict__ any_fail)
 {
-    constexpr int CAP = THREADS * PER, NB = 2 * CAP;
+    constexpr int CAP = THREADS * PER, NB = ESC_BPP * CAP, WPT = ESC_BPP * PER / 2;   // WPT counter words per thread
     extern __shared__ __align__(16) unsigned char s_raw[];
     double *sval = reinterpret_cast<double *>(s_raw);
     int32_t *skey = reinterpret_cast<int32_t *>(s_raw + sizeof(double) * CAP);
@@ -375,8 +376,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *
         int32_t *oc = ecol + off;
         double *ov = eval + off;
 #pragma unroll
-        for (int q = 0; q < PER; q++)
-            cntw[tid * PER + q] = 0;
+        for (int q = 0; q < WPT; q++)
+            cntw[tid + q * THREADS] = 0;
         if (tid == 0) {
             s_min = INT32_MAX;
             s_max = -1;
@@ -425,11 +426,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *
             }
         __syncthreads();
         {
-            unsigned loc[PER];
+            unsigned loc[WPT];
             int sum = 0, big = 0;
 #pragma unroll
-            for (int q = 0; q < PER; q++) {
-                loc[q] = cntw[tid * PER + q];
+            for (int q = 0; q < WPT; q++) {
+                loc[q] = cntw[tid * WPT + q];
                 const int lo = (int)(loc[q] & 0xffffu), hi = (int)(loc[q] >> 16);
                 sum += lo + hi;
                 big |= (lo > ESC_BUCKET_MAX) | (hi > ESC_BUCKET_MAX);
@@ -439,9 +440,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *
             int tot;
             int ex = block_exclusive_scan<int>(sum, s_wt, tot);
 #pragma unroll
-            for (int q = 0; q < PER; q++) {
+            for (int q = 0; q < WPT; q++) {
                 const int lo = (int)(loc[q] & 0xffffu), hi = (int)(loc[q] >> 16);
-                cntw[tid * PER + q] = (unsigned)ex | (unsigned)(ex + lo) << 16;
+                cntw[tid * WPT + q] = (unsigned)ex | (unsigned)(ex + lo) << 16;
                 ex += lo + hi;
             }
             if (tid == THREADS - 1)
@@ -464,11 +465,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *
                 sval[pos] = v[q];
             }
         __syncthreads();
-        const int s0 = (int)cnt16[tid * 2 * PER], s1 = (int)cnt16[(tid + 1) * 2 * PER];
-        int w = s0;   // the piece's sorted entries live in [s0, w)
+        const int s0 = (int)cnt16[tid * 2 * WPT], s1 = (int)cnt16[(tid + 1) * 2 * WPT];
+        int w = s0, ndup = 0;   // the piece's sorted entries live in [s0, w); ndup of them repeat a column
         {
             int32_t last = -1;
-            bool dup = false;
             for (int i = s0; i < s1; i++) {
                 const int32_t ki = skey[i];
                 if (ki > last) {
@@ -481,39 +481,37 @@ __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *
                     const double vi = sval[i];
                     const long long bi = __double_as_longlong(vi);
                     int j = w - 1;
-                    while (j >= s0 && (skey[j] > ki || (skey[j] == ki && __double_as_longlong(sval[j]) > bi))) {
-                        skey[j + 1] = skey[j];
-                        sval[j + 1] = sval[j];
+                    bool eq = false;
+                    while (j >= s0) {
+                        const int32_t kj = skey[j];
+                        if (kj < ki)
+                            break;
+                        const double vj = sval[j];
+                        if (kj == ki) {
+                            eq = true;
+                            if (__double_as_longlong(vj) <= bi)
+                                break;
+                        }
+                        skey[j + 1] = kj;
+                        sval[j + 1] = vj;
                         j--;
                     }
                     skey[j + 1] = ki;
                     sval[j + 1] = vi;
-                    dup |= (j >= s0 && skey[j] == ki) || (j + 1 < w && skey[j + 2] == ki);
+                    ndup += eq;
                 }
                 w++;
             }
-            if (dup) {
-                int m = s0;
-                for (int i = s0; i < w; i++) {
-                    const int32_t ki = skey[i];
-                    if (m > s0 && skey[m - 1] == ki)
-                        sval[m - 1] += sval[i];
-                    else {
-                        if (m != i) {
-                            skey[m] = ki;
-                            sval[m] = sval[i];
-                        }
-                        m++;
-                    }
-                }
-                w = m;
-            }
         }
         int tot;
-        const int ex = block_exclusive_scan<int>(w - s0, s_wt, tot);
-        for (int i = s0; i < w; i++) {
-            oc[ex + (i - s0)] = skey[i];
-            ov[ex + (i - s0)] = sval[i];
+        int out = block_exclusive_scan<int>(w - s0 - ndup, s_wt, tot);
+        for (int i = s0; i < w; out++) {   // equal columns are adjacent and ordered by value: summed in that order
+            const int32_t ki = skey[i];
+            double acc = sval[i];
+            for (i++; i < w && skey[i] == ki; i++)
+                acc += sval[i];
+            oc[out] = ki;
+            ov[out] = acc;
         }
         if (tid == 0)
             pnnz[p] = tot;
@@ -802,21 +800,21 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     // bucket sort + merge, then the hash kernel for what it flagged (usually nothing: its CTAs only read the flags)
     if (cnt[2]) {
         auto k = k_esc_sortmerge<128, 4, 8>;
-        CSRK_LAUNCH(k, (unsigned)std::min(cnt[2], sms * 32), 128, 512 * 16 + 16, s, PL + off[2], cnt[2], po, ec, ev, pz, fl, af);
+        CSRK_LAUNCH(k, (unsigned)std::min(cnt[2], sms * 32), 128, 512 * 20 + 16, s, PL + off[2], cnt[2], po, ec, ev, pz, fl, af);
         auto h = k_esc_reduce<1024, 128, 512>;
         CSRK_LAUNCH(h, (unsigned)std::min(cnt[2], sms * 8), 128, 1024 * 12 + 512 * 4, s, PL + off[2], cnt[2], po, ec, ev, pz, fl, af);
     }
     if (cnt[3]) {
         auto k = k_esc_sortmerge<256, 8, 5>;
-        CSRK_LAUNCH(k, (unsigned)std::min(cnt[3], sms * 16), 256, 2048 * 16 + 16, s, PL + off[3], cnt[3], po, ec, ev, pz, fl, af);
+        CSRK_LAUNCH(k, (unsigned)std::min(cnt[3], sms * 16), 256, 2048 * 20 + 16, s, PL + off[3], cnt[3], po, ec, ev, pz, fl, af);
         auto h = k_esc_reduce<4096, 256, 2048>;
         CSRK_TRY(optin_smem(h, 4096 * 12 + 2048 * 4));
         CSRK_LAUNCH(h, (unsigned)std::min(cnt[3], sms * 4), 256, 4096 * 12 + 2048 * 4, s, PL + off[3], cnt[3], po, ec, ev, pz, fl, af);
     }
     if (cnt[4]) {
         auto k = k_esc_sortmerge<512, 16, 1>;
-        CSRK_TRY(optin_smem(k, 8192 * 16 + 16));
-        CSRK_LAUNCH(k, (unsigned)std::min(cnt[4], sms), 512, 8192 * 16 + 16, s, PL + off[4], cnt[4], po, ec, ev, pz, fl, af);
+        CSRK_TRY(optin_smem(k, 8192 * 20 + 16));
+        CSRK_LAUNCH(k, (unsigned)std::min(cnt[4], sms), 512, 8192 * 20 + 16, s, PL + off[4], cnt[4], po, ec, ev, pz, fl, af);
         auto h = k_esc_reduce<16384, 512, 4096>;
         CSRK_TRY(optin_smem(h, 16384 * 12 + 4096 * 4));
         CSRK_LAUNCH(h, (unsigned)std::min(cnt[4], sms), 512, 16384 * 12 + 4096 * 4, s, PL + off[4], cnt[4], po, ec, ev, pz, fl, af);
