@@ -48,6 +48,7 @@ SIGNATURES = {
     "csrk_spgemm_abt": (_int, [_vp, _vp, _P(_vp)]),
     "csrk_spgemm_stats": (_int, [_vp, _P(_i64), _P(_i64)]),
     "csrk_spgemm_path": (_int, [_vp, _P(_int)]),
+    "csrk_spgemm_side_list": (_int, [_vp, _P(_i64)]),
     "csrk_normalize_rows": (_int, [_vp, _int, _vp, _vp]),
     "csrk_from_coo": (_int, [_i32, _i32, _i64, _vp, _vp, _vp, _int, _P(_vp)]),
     "csrk_transpose": (_int, [_vp, _int, _P(_vp)]),

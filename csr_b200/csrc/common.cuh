@@ -143,6 +143,7 @@ struct Options {
     std::atomic<int64_t> sym_bytes{1};                  // SpGEMM symbolic pass of heavy rows: byte marks with plain stores when the columns fit
     std::atomic<int64_t> spgemm_fixed{1};               // SpGEMM heavy rows: fixed-point atomics when the value range allows
     std::atomic<int64_t> own_chunk_prod{0};             // SpGEMM heavy-row chunking: 0 auto, > 0 products per chunk, < 0 off
+    std::atomic<int64_t> fix_tiny_cap{0};               // > 0: capacity (entries) of the fixed-point kernel's side list (tests force an overflow)
     std::atomic<int64_t> spgemm_esc{1};                 // SpGEMM expand/sort/compress path: 0 off, 1 for wide results, 2 always (tests)
     std::atomic<int64_t> esc_target{1536};              // products per pseudo-row (row x column range) of that path
     std::atomic<int64_t> esc_budget{0};                 // > 0: cap in bytes on its expansion (else: half of the free memory)
@@ -161,7 +162,7 @@ struct csrk_matrix {
     int32_t *ci = nullptr;  // int32[nnz]
     void *vs = nullptr;     // float[nnz] / double[nnz] / nullptr
     int val_kind = 0;       // 0, 4, 8
-    int64_t stat_products = -1, stat_out_nnz = -1;
+    int64_t stat_products = -1, stat_out_nnz = -1, stat_tiny = 0;   // stat_tiny: products that went through the fixed-point kernel's side list
     int stat_path = 0;  // dense numeric path of the product that made this matrix: 0 none, 1 owner-computes, 2 fixed point
     csrk::SpmvPlan *plan = nullptr;  // lazily built SpMV tile map
     csrk::StreamPlan *stream[2] = {nullptr, nullptr};  // lazily built stream plans for float32 / float64 x

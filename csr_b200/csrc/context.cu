@@ -407,6 +407,9 @@ int csrk_set_option(const char *name, int64_t value)
         options().spgemm_fixed = value ? 1 : 0;
     } else if (!strcmp(name, "own_chunk_prod")) {
         options().own_chunk_prod = value;
+    } else if (!strcmp(name, "fix_tiny_cap")) {
+        CSRK_ARG(value >= 0, "fix_tiny_cap is an entry count (0 = 1/32 of the products)");
+        options().fix_tiny_cap = value;
     } else if (!strcmp(name, "spgemm_esc")) {
         CSRK_ARG(value >= 0 && value <= 2, "spgemm_esc must be 0 (off), 1 (wide results) or 2 (always)");
         options().spgemm_esc = value;
@@ -740,6 +743,13 @@ int csrk_spgemm_path(csrk_h c, int *path)
 {
     CSRK_ARG(c != nullptr && path != nullptr, "NULL argument");
     *path = c->stat_path;
+    return CSRK_OK;
+}
+
+int csrk_spgemm_side_list(csrk_h c, int64_t *entries)
+{
+    CSRK_ARG(c != nullptr && entries != nullptr, "NULL argument");
+    *entries = c->stat_tiny;
     return CSRK_OK;
 }
 

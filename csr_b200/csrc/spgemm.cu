@@ -999,44 +999,115 @@ k_own_combine(const int32_t *__restrict__ rows, int nbin, const int *__restrict_
 // stated the way a re-ordered floating-point sum is bounded).  For non-negative operands that is the relative
 // error of the element itself; signs are welcome (two's-complement words), a wide dynamic range is not --
 // mean-centred ratings have values arbitrarily close to 0, so min|a*b| is tiny -- and takes the owner kernel.
-struct ValStats {
-    unsigned long long min_bits, max_bits;  // bit patterns of the smallest non-zero and the largest |v|
-    int negative, nonfinite;
-};
-
-__global__ void __launch_bounds__(256) k_val_stats(const void *__restrict__ vs, int vk, int64_t nnz, ValStats *__restrict__ st)
+// Equilibration (round 2).  A fixed scale per row only covers operands whose magnitudes span a few bits, and the
+// interesting inputs of A*B^T do not: unit-normalised rows (cosine similarity) differ by the rows' norms,
+// mean-centred ratings come arbitrarily close to 0.  So the operands are first brought to a common magnitude
+// with exact power-of-two factors: ea[i] = frexp exponent of the largest |a_ik| of A's row i, eb[j] the same for
+// B's COLUMN j; the kernel multiplies a_ik * 2^-ea[i] (folded into the row's scale) with b'_kj = b_kj * 2^-eb[j]
+// (a scaled copy of B's values), so every product is below 1 in magnitude, accumulates T = rn(p' * 2^(62 - hb_i))
+// and the sweep multiplies the sum by 2^(ea[i] + eb[j] - 62 + hb_i).  A product with |T| < 2^35 -- one whose
+// rounding error would exceed 2^-36 of its own magnitude -- is NOT added: it goes, exactly, to a side list
+// (row, column, p') and k_fix_tiny adds it to the finished element in float64.  Every other term carries an error
+// below 2^-36 of its magnitude, so every output element is within 2^-35 * sum_k |a_ik||b_kj| whatever the values
+// are; the gate only asks for finite operands whose exponents stay within +-400.
+__global__ void __launch_bounds__(256) k_row_expo(MatView A, int *__restrict__ ea)
 {
-    unsigned long long lo = ~0ull, hi = 0ull;
-    int neg = 0, bad = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
-        const double v = ld_val(vs, vk, i);
-        if (!isfinite(v))
-            bad = 1;
-        else if (v != 0.0) {
-            if (v < 0.0)
-                neg = 1;
-            const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
-            lo = min(lo, b);
-            hi = max(hi, b);
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= A.nrows)
+        return;
+    const int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
+    int e = INT32_MIN;
+    for (int64_t k = as + lane; k < ae; k += 32) {
+        const double v = ld_val(A.vs, A.vk, k);
+        if (v != 0.0)
+            e = max(e, (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1022);   // |v| < 2^e (Inf/NaN: 1025)
+    }
+    e = __reduce_max_sync(0xffffffffu, e);
+    if (lane == 0)
+        ea[row] = e;
+}
+__global__ void __launch_bounds__(256) k_col_expo(MatView B, int *__restrict__ eb)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < B.nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        const double v = ld_val(B.vs, B.vk, k);
+        if (v != 0.0)
+            atomicMax(&eb[B.ci[k]], (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1022);
+    }
+}
+__global__ void __launch_bounds__(256) k_fill_i32(int *__restrict__ p, int64_t n, int v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        p[i] = v;
+}
+// smallest and largest exponent of the non-empty rows / columns
+__global__ void __launch_bounds__(256) k_expo_range(const int *__restrict__ e, int n, int *__restrict__ mm)
+{
+    int lo = INT32_MAX, hi = INT32_MIN;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = e[i];
+        if (v != INT32_MIN) {
+            lo = min(lo, v);
+            hi = max(hi, v);
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        neg |= __shfl_xor_sync(0xffffffffu, neg, o);
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0 && hi != INT32_MIN) {
+        atomicMin(&mm[0], lo);
+        atomicMax(&mm[1], hi);
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (hi) {
-            atomicMin(&st->min_bits, lo);
-            atomicMax(&st->max_bits, hi);
+}
+__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }   // |e| < 1023
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_cols(const int32_t *__restrict__ ci, const void *__restrict__ vs, int vk, int64_t nnz,
+                                                     const int *__restrict__ eb, T *__restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) {
+        const int e = eb[ci[k]];
+        out[k] = (T)(ld_val(vs, vk, k) * (e == INT32_MIN ? 1.0 : pow2(-e)));   // exact: a power of two
+    }
+}
+
+// side list of the fixed-point kernel: warps reserve blocks of 32 entries (one global atomic per block)
+struct TinyEnt {
+    int32_t row, col;
+    double p;   // the equilibrated product a' * b' (numba's product, scaled by an exact power of two)
+};
+struct TinyList {
+    TinyEnt *buf;
+    unsigned long long *count;   // entries reserved (blocks of 32; may run past cap: the host checks)
+    unsigned long long cap;
+};
+// all 32 lanes call this together; `has` lanes append one entry each
+__device__ __forceinline__ void tiny_append(const TinyList &t, bool has, int32_t row, int32_t col, double p,
+                                            unsigned long long *s_base, int *s_used, int warp, int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (!m)
+        return;
+    const int k = __popc(m);
+    int used = s_used[warp];
+    if (used + k > 32) {   // a new block; what is left of the old one stays marked empty
+        if (lane == 0) {
+            s_base[warp] = atomicAdd(t.count, 32ull);
+            s_used[warp] = 0;
         }
-        if (neg)
-            st->negative = 1;
-        if (bad)
-            st->nonfinite = 1;
+        __syncwarp();
+        const unsigned long long b = s_base[warp];
+        if (b + lane < t.cap)
+            t.buf[b + lane].row = -1;
+        __syncwarp();
+        used = 0;
     }
+    const unsigned long long idx = s_base[warp] + used + __popc(m & lanemask_lt());
+    if (has && idx < t.cap)
+        t.buf[idx] = TinyEnt{row, col, p};
+    __syncwarp();
+    if (lane == 0)
+        s_used[warp] = used + k;
+    __syncwarp();
 }
 
 __device__ __forceinline__ int headroom_bits(int64_t len)
@@ -1052,7 +1123,8 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
             int32_t *__restrict__ c_ci, double *__restrict__ c_vs, int both_f32, int n_cols, int win, int passes,
             int *__restrict__ work_counter, const unsigned *__restrict__ keep, const int32_t *__restrict__ keep_slot,
             const int32_t *__restrict__ psplit, const int *__restrict__ item_off, const int *__restrict__ chunk_base,
-            int nitems, long long *__restrict__ partial, int e0)
+            int nitems, long long *__restrict__ partial, const int *__restrict__ ea, const int *__restrict__ eb, int eb_u,
+            TinyList tiny)
 {
     static_assert(THREADS * 2 * 32 >= DENSE_WIN, "two bitmap words per thread must cover a window");
     static_assert(THREADS % 32 == 0 && THREADS <= 1024, "whole warps");
@@ -1062,9 +1134,13 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
     __shared__ int s_wt[33];
     __shared__ unsigned s_bits[2 * THREADS];
     __shared__ int s_wpre[2 * THREADS];
+    __shared__ unsigned long long s_tbase[THREADS / 32];
+    __shared__ int s_tused[THREADS / 32];
     unsigned *slo = reinterpret_cast<unsigned *>(s_raw), *shi = slo + win;
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr int NWARP = THREADS / 32;
+    if (lane == 0)
+        s_tused[tid >> 5] = 32;   // no block yet
     const int n_words = (n_cols + 31) >> 5;
     for (int i = tid; i < 2 * win; i += THREADS)
         slo[i] = 0u;
@@ -1094,9 +1170,15 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
         const int chunk = s_idx - item_off[ri], nch = item_off[ri + 1] - item_off[ri];
         const int32_t row = rows[ri];
         int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
-        const int sh = e0 - headroom_bits(ae - as);  // the WHOLE row's length: all chunks share one scale
-        const double scale = __longlong_as_double((long long)(1023 + sh) << 52);   // 2^sh
-        const double inv_scale = __longlong_as_double((long long)(1023 - sh) << 52);
+        const int hbits = headroom_bits(ae - as);  // the WHOLE row's length: all chunks share one scale
+        const int ea_i = ea[row];                  // (a heavy row has products, but all its values may be 0)
+        // eb == nullptr: all of B's columns share the exponent eb_u (raw or centred ratings): B is read as it is
+        // and 2^-eb_u is folded into the row's factor
+        const int ea_f = (ea_i == INT32_MIN ? 0 : ea_i) + (eb ? 0 : eb_u);
+        const int sh = 62 - hbits - ea_f;
+        const double scale = pow2(sh);             // a_ik * 2^sh: equilibrated and scaled at once (float64 operands)
+        const double scale_f = pow2(62 - hbits), eq_a = pow2(-ea_f);   // float32 operands: product first
+        const double inv_scale = pow2(-sh);
         if (nch > 1) {
             const int64_t len = ae - as;
             ae = as + len * (chunk + 1) / nch;
@@ -1140,7 +1222,7 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
                 for (int t = 0; t < cnt; t++) {
                     const int64_t pbs = __shfl_sync(0xffffffffu, bs, t);
                     const int plen = __shfl_sync(0xffffffffu, len, t);
-                    const double pav = __shfl_sync(0xffffffffu, av, t) * (both_f32 ? 1.0 : scale);
+                    const double pav = __shfl_sync(0xffffffffu, av, t) * (both_f32 ? eq_a : scale);
                     for (int k0 = 0; k0 < plen; k0 += 128) {
                         int col[4];
                         double val[4];
@@ -1154,17 +1236,28 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
                                 val[u] = ld_val(B.vs, B.vk, pbs + k);
                             }
                         }
+                        unsigned small = 0;   // bit u: product u is below the accumulator's grid
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            if (col[u] >= 0) {
-                                // (float64 operands: the row's scale is a power of two folded into a, exactly)
-                                const double pr = both_f32 ? (double)__fmul_rn((float)pav, (float)val[u]) * scale
-                                                           : __dmul_rn(pav, val[u]);
-                                const long long T = __double2ll_rn(pr);
+                            // (float64 operands: the row's scale is a power of two folded into a, exactly; a lane
+                            // past the end of the piece has val = 0: T = 0, nothing happens)
+                            const double pr = both_f32 ? (double)__fmul_rn((float)pav, (float)val[u]) * scale_f
+                                                       : __dmul_rn(pav, val[u]);
+                            const long long T = __double2ll_rn(pr);
+                            const bool big = fabs(pr) >= 34359738368.0;   // 2^35: |T| >= 2^35, rounding error <= 2^-36 |term|
+                            val[u] = pr;
+                            small |= (unsigned)(!big && pr != 0.0) << u;
+                            if (big) {   // (kept this short: two predicated atomics, the four chains overlap)
                                 const unsigned tlo = (unsigned)T, thi = (unsigned)((unsigned long long)T >> 32);
                                 const unsigned old = atomicAdd(&slo[col[u] - c0], tlo);
                                 atomicAdd(&shi[col[u] - c0], thi + ((old + tlo) < old ? 1u : 0u));
                             }
+                        }
+                        // rounded too coarsely for the accumulator: exact side list (rare; one vote per 128 entries)
+                        if (__any_sync(0xffffffffu, small != 0)) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++)
+                                tiny_append(tiny, (small >> u) & 1u, row, col[u], val[u], s_tbase, s_tused, tid >> 5, lane);
                         }
                     }
                 }
@@ -1193,16 +1286,34 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
                 s_wpre[THREADS + tid] = tot0 + ex1;
             }
             __syncthreads();
-            for (int col = tid; col < c1 - c0; col += THREADS) {
-                const unsigned bits = s_bits[col >> 5];
-                const unsigned bit = 1u << (col & 31);
-                if (bits & bit) {
-                    const int64_t o = out + s_wpre[col >> 5] + __popc(bits & (bit - 1u));
-                    const long long v = (long long)(((unsigned long long)shi[col] << 32) | slo[col]);
-                    __stcs(&c_ci[o], c0 + col);  // streaming: the 12 B/entry result must not evict B from L2
-                    __stcs(&c_vs[o], (double)v * inv_scale);
-                    slo[col] = 0u;
-                    shi[col] = 0u;
+            // (four columns per thread and step: the four loads of the columns' exponents are in flight together)
+            for (int col0 = tid; col0 < c1 - c0; col0 += 4 * THREADS) {
+                int ecol[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int col = col0 + u * THREADS;
+                    ecol[u] = 0;
+                    if (eb && col < c1 - c0)
+                        ecol[u] = eb[c0 + col];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int col = col0 + u * THREADS;
+                    if (col >= c1 - c0)
+                        break;
+                    const unsigned bits = s_bits[col >> 5];
+                    const unsigned bit = 1u << (col & 31);
+                    if (bits & bit) {
+                        const int64_t o = out + s_wpre[col >> 5] + __popc(bits & (bit - 1u));
+                        const long long v = (long long)(((unsigned long long)shi[col] << 32) | slo[col]);
+                        __stcs(&c_ci[o], c0 + col);  // streaming: the 12 B/entry result must not evict B from L2
+                        double r = (double)v * inv_scale;
+                        if (eb)
+                            r *= pow2(ecol[u] == INT32_MIN ? 0 : ecol[u]);
+                        __stcs(&c_vs[o], r);
+                        slo[col] = 0u;
+                        shi[col] = 0u;
+                    }
                 }
             }
             out += tot0 + tot1;
@@ -1216,7 +1327,7 @@ __global__ void __launch_bounds__(256)
 k_fix_combine(MatView A, const int32_t *__restrict__ rows, int nbin, const int *__restrict__ item_off,
               const int *__restrict__ chunk_base, const long long *__restrict__ partial, int n_cols, int win, int passes,
               const unsigned *__restrict__ keep, const int32_t *__restrict__ keep_slot, const int64_t *__restrict__ c_rp,
-              int32_t *__restrict__ c_ci, double *__restrict__ c_vs, int e0)
+              int32_t *__restrict__ c_ci, double *__restrict__ c_vs, const int *__restrict__ ea, const int *__restrict__ eb, int eb_u)
 {
     __shared__ int s_wt[33];
     const int ri = blockIdx.x / passes, q = blockIdx.x % passes;
@@ -1225,8 +1336,10 @@ k_fix_combine(MatView A, const int32_t *__restrict__ rows, int nbin, const int *
         return;
     const int tid = threadIdx.x;
     const int32_t row = rows[ri];
-    const int sh = e0 - headroom_bits(ld_rp(A.rp, A.rp64, (int64_t)row + 1) - ld_rp(A.rp, A.rp64, row));
-    const double inv_scale = __longlong_as_double((long long)(1023 - sh) << 52);
+    const int ea_i = ea[row];
+    const int sh = 62 - headroom_bits(ld_rp(A.rp, A.rp64, (int64_t)row + 1) - ld_rp(A.rp, A.rp64, row)) -
+                   (ea_i == INT32_MIN ? 0 : ea_i) - (eb ? 0 : eb_u);
+    const double inv_scale = pow2(-sh);
     const int n_words = (n_cols + 31) >> 5;
     const unsigned *kept = keep + (size_t)keep_slot[row] * n_words;
     const int c0 = q * win, c1 = min(c0 + win, n_cols);
@@ -1253,12 +1366,38 @@ k_fix_combine(MatView A, const int32_t *__restrict__ rows, int nbin, const int *
             for (int ch = 0; ch < nch; ch++)
                 v += p0[ch * cstride + kl];
             c_ci[o] = c0 + kl;
-            c_vs[o] = (double)v * inv_scale;
+            const int e = eb ? eb[c0 + kl] : 0;
+            c_vs[o] = (double)v * inv_scale * pow2(e == INT32_MIN ? 0 : e);
             o++;
         }
         out += tot;
         __syncthreads();
     }
+}
+
+// the side list: every entry is added, in float64, to its (finished) output element
+__global__ void __launch_bounds__(256)
+k_fix_tiny(const TinyEnt *__restrict__ buf, unsigned long long n, MatView A, const int *__restrict__ ea, const int *__restrict__ eb,
+           int eb_u, const void *__restrict__ c_rp, int c_rp64, const int32_t *__restrict__ c_ci, double *__restrict__ c_vs)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const TinyEnt t = buf[i];
+    if (t.row < 0)
+        return;
+    const int ea_i = ea[t.row], eb_j = eb ? eb[t.col] : 0;
+    const int sh = 62 - headroom_bits(ld_rp(A.rp, A.rp64, (int64_t)t.row + 1) - ld_rp(A.rp, A.rp64, t.row)) -
+                   (ea_i == INT32_MIN ? 0 : ea_i) - (eb ? 0 : eb_u);
+    int64_t lo = ld_rp(c_rp, c_rp64, t.row), hi = ld_rp(c_rp, c_rp64, (int64_t)t.row + 1);
+    while (lo < hi) {   // the column exists: the symbolic pass saw this product
+        const int64_t mid = (lo + hi) >> 1;
+        if (c_ci[mid] < t.col)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    atomicAdd(&c_vs[lo], t.p * pow2(-sh) * pow2(eb_j == INT32_MIN ? 0 : eb_j));
 }
 
 __global__ void k_fix_bounds(int n, int win, int passes, int32_t *__restrict__ bounds)
@@ -1551,51 +1690,81 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
             CSRK_LAUNCH(k, (unsigned)ncnt[4], 512, NUM_C3 * 12 + 4096 * 4, s, A, B, NL + noff[4], crp, out->ci, cvs,
                         both_f32);
         }
-        if (ncnt[5]) {
+        // heavy rows; a second attempt (without the fixed-point kernel) only if its side list overflowed
+        for (int attempt = 0; ncnt[5] && attempt < 2; attempt++) {
             int *wc = counter.as<int>() + 1;
+            if (attempt)
+                CSRK_CUDA(cudaMemsetAsync(wc, 0, sizeof(int), s));
             const unsigned *kp = keep.as<unsigned>();
             const int32_t *ks = keep_slot.as<int32_t>();
             const int passes = (int)div_up((int64_t)n, DENSE_WIN);
             bool owner = passes <= DENSE_MAX_PASSES && kp != nullptr && n >= 1024;
             bool fixed = false;
-            int e0 = 0;
+            DevBuf ea, eb, bscaled, tiny_buf, tiny_cnt;
+            TinyList tiny{nullptr, nullptr, 0};
+            MatView Bs = B;   // B with its values equilibrated by column (fixed-point kernel)
+            bool eb_uniform = false;
+            int eb_u = 0;
             if (owner) {
                 // both dense kernels walk B's rows by column range: rows strictly increasing in column
-                DevBuf flag, vstats;
+                DevBuf flag, erange;
                 CSRK_TRY(flag.alloc_zero(sizeof(int), s));
                 if (b->nnz > 1)
                     CSRK_LAUNCH(k_rows_not_strict, (unsigned)div_up(b->nnz - 1, 256), 256, 0, s, B, flag.as<int>());
-                // value range of both operands: decides whether the fixed-point accumulator is exact enough
-                const bool want_fixed = options().spgemm_fixed.load() != 0;
-                ValStats vs_h[2] = {{~0ull, 0ull, 0, 0}, {~0ull, 0ull, 0, 0}};
+                // fixed-point accumulator: needs finite operands of sane exponents (see the equilibration note)
+                int hb = 0;
+                for (unsigned long long l = PM[2]; l; l >>= 1)
+                    hb++;  // ceil(log2(longest row + 1)): terms per output element
+                const bool want_fixed = attempt == 0 && options().spgemm_fixed.load() != 0 && hb <= 24 && passes <= FIX_MAX_PASSES;
+                int er[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};   // min / max exponent: A's rows, B's columns
                 if (want_fixed) {
-                    CSRK_TRY(vstats.alloc(sizeof vs_h, s));
-                    CSRK_CUDA(cudaMemcpyAsync(vstats.p, vs_h, sizeof vs_h, cudaMemcpyHostToDevice, s));
-                    CSRK_LAUNCH(k_val_stats, (unsigned)std::min<int64_t>(div_up(a->nnz, 256), (int64_t)sms * 8), 256, 0, s, a->vs,
-                                a->val_kind, a->nnz, vstats.as<ValStats>());
-                    CSRK_LAUNCH(k_val_stats, (unsigned)std::min<int64_t>(div_up(b->nnz, 256), (int64_t)sms * 8), 256, 0, s, b->vs,
-                                b->val_kind, b->nnz, vstats.as<ValStats>() + 1);
-                    CSRK_CUDA(cudaMemcpyAsync(vs_h, vstats.p, sizeof vs_h, cudaMemcpyDeviceToHost, s));
+                    CSRK_TRY(ea.alloc(sizeof(int) * (size_t)m, s));
+                    CSRK_TRY(eb.alloc(sizeof(int) * (size_t)n, s));
+                    CSRK_TRY(erange.alloc(sizeof er, s));
+                    CSRK_CUDA(cudaMemcpyAsync(erange.p, er, sizeof er, cudaMemcpyHostToDevice, s));
+                    CSRK_LAUNCH(k_fill_i32, (unsigned)div_up((int64_t)n, 256), 256, 0, s, eb.as<int>(), (int64_t)n, INT32_MIN);
+                    CSRK_LAUNCH(k_row_expo, (unsigned)div_up((int64_t)m * 32, 256), 256, 0, s, A, ea.as<int>());
+                    CSRK_LAUNCH(k_col_expo, (unsigned)std::min<int64_t>(div_up(b->nnz, 256), (int64_t)sms * 16), 256, 0, s, B,
+                                eb.as<int>());
+                    CSRK_LAUNCH(k_expo_range, (unsigned)std::min<int64_t>(div_up((int64_t)m, 256), (int64_t)sms * 4), 256, 0, s,
+                                ea.as<int>(), (int)m, erange.as<int>());
+                    CSRK_LAUNCH(k_expo_range, (unsigned)std::min<int64_t>(div_up((int64_t)n, 256), (int64_t)sms * 4), 256, 0, s,
+                                eb.as<int>(), (int)n, erange.as<int>() + 2);
+                    CSRK_CUDA(cudaMemcpyAsync(er, erange.p, sizeof er, cudaMemcpyDeviceToHost, s));
                 }
                 int bad = 0;
                 CSRK_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
                 CSRK_CUDA(cudaStreamSynchronize(s));
                 owner = !bad;
-                if (owner && want_fixed && !vs_h[0].nonfinite && !vs_h[1].nonfinite &&
-                    vs_h[0].max_bits && vs_h[1].max_bits) {
-                    double lim[4];
-                    const unsigned long long bits[4] = {vs_h[0].min_bits, vs_h[0].max_bits, vs_h[1].min_bits, vs_h[1].max_bits};
-                    memcpy(lim, bits, sizeof lim);
-                    const double pmin = lim[0] * lim[2], pmax = lim[1] * lim[3];
-                    int hb = 0;
-                    for (unsigned long long l = PM[2]; l; l >>= 1)
-                        hb++;  // ceil(log2(longest row + 1)): terms per output element
-                    int x = 0;
-                    (void)frexp(pmax, &x);  // pmax <= 2^x
-                    // error of an output element <= (pmax / pmin) * 2^(hb - 61) * sum|terms|; keep it below 2^-35
-                    if (hb <= 24 && passes <= FIX_MAX_PASSES && pmin > 1e-280 && pmax < 1e280 && pmax / pmin <= ldexp(1.0, 26 - hb)) {
+                if (owner && want_fixed && er[1] != INT32_MIN && er[3] != INT32_MIN && er[0] >= -400 && er[1] <= 400 &&
+                    er[2] >= -400 && er[3] <= 400) {
+                    // the scaled copy of B's values (its own dtype: a power-of-two factor is exact in either) and
+                    // the side list: room for 1/32 of the products, from the pool (it goes back after the call)
+                    const int bvk = b->val_kind == 4 ? 4 : 8;
+                    const unsigned long long cap =
+                        (unsigned long long)std::min<int64_t>(std::max<int64_t>((int64_t)(P / 32), (int64_t)1 << 20), (int64_t)1 << 28);
+                    const int64_t opt_cap = options().fix_tiny_cap.load();
+                    tiny.cap = opt_cap > 0 ? (unsigned long long)opt_cap : cap;
+                    eb_uniform = er[2] == er[3];   // every column of B peaks at the same exponent: no scaled copy
+                    eb_u = er[2];
+                    if ((eb_uniform || bscaled.alloc((size_t)b->nnz * bvk, s) == CSRK_OK) &&
+                        tiny_buf.alloc_owned(sizeof(TinyEnt) * (size_t)tiny.cap, s) == CSRK_OK &&
+                        tiny_cnt.alloc_zero(sizeof(unsigned long long), s) == CSRK_OK) {
+                        if (eb_uniform)
+                            ;
+                        else if (bvk == 4)
+                            CSRK_LAUNCH(k_scale_cols<float>, (unsigned)div_up(b->nnz, 256), 256, 0, s, b->ci, b->vs, b->val_kind,
+                                        b->nnz, eb.as<int>(), bscaled.as<float>());
+                        else
+                            CSRK_LAUNCH(k_scale_cols<double>, (unsigned)div_up(b->nnz, 256), 256, 0, s, b->ci, b->vs, b->val_kind,
+                                        b->nnz, eb.as<int>(), bscaled.as<double>());
+                        if (!eb_uniform) {
+                            Bs.vs = bscaled.p;
+                            Bs.vk = bvk;
+                        }
+                        tiny.buf = tiny_buf.as<TinyEnt>();
+                        tiny.count = tiny_cnt.as<unsigned long long>();
                         fixed = true;
-                        e0 = 62 - x;
                     }
                 }
             }
@@ -1642,32 +1811,43 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                 const int64_t ncomb = tots[2];  // chunked rows sit at the head of the LPT-ordered list
                 CSRK_TRACE_MARK("spgemm: light bins + dense prep (value range, bounds, split, items)", s);
                 if (fixed) {
+                    const int *ebp = eb_uniform ? nullptr : eb.as<int>();
                     const int64_t ft = options().fix_threads.load();
                     if (ft == 1024) {
                         auto k = k_num_fixed<1024>;
                         CSRK_TRY(optin_smem(k, bytes));
-                        CSRK_LAUNCH(k, (unsigned)grid, 1024, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                        CSRK_LAUNCH(k, (unsigned)grid, 1024, bytes, s, A, Bs, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                                     (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
-                                    chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                                    chunk_base.as<int>(), nitems, partial.as<long long>(), ea.as<int>(), ebp, eb_u, tiny);
                     } else if (ft == 768) {
                         auto k = k_num_fixed<768>;
                         CSRK_TRY(optin_smem(k, bytes));
-                        CSRK_LAUNCH(k, (unsigned)grid, 768, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                        CSRK_LAUNCH(k, (unsigned)grid, 768, bytes, s, A, Bs, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                                     (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
-                                    chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                                    chunk_base.as<int>(), nitems, partial.as<long long>(), ea.as<int>(), ebp, eb_u, tiny);
                     } else {
                         auto k = k_num_fixed<512>;
                         CSRK_TRY(optin_smem(k, bytes));
-                        CSRK_LAUNCH(k, (unsigned)grid, 512, bytes, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
+                        CSRK_LAUNCH(k, (unsigned)grid, 512, bytes, s, A, Bs, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                                     (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
-                                    chunk_base.as<int>(), nitems, partial.as<long long>(), e0);
+                                    chunk_base.as<int>(), nitems, partial.as<long long>(), ea.as<int>(), ebp, eb_u, tiny);
                     }
                     if (nparts) {
                         CSRK_TRACE_MARK("spgemm: numeric (fixed-point kernel)", s);
                         CSRK_LAUNCH(k_fix_combine, (unsigned)(ncomb * passes), 256, 0, s, A, NL + noff[5], ncnt[5],
                                     item_off.as<int>(), chunk_base.as<int>(), partial.as<long long>(), (int)n, win, passes, kp,
-                                    ks, crp, out->ci, cvs, e0);
+                                    ks, crp, out->ci, cvs, ea.as<int>(), ebp, eb_u);
                     }
+                    // the side list: how many entries, and did they fit?
+                    unsigned long long n_tiny = 0;
+                    CSRK_CUDA(cudaMemcpyAsync(&n_tiny, tiny.count, sizeof n_tiny, cudaMemcpyDeviceToHost, s));
+                    CSRK_CUDA(cudaStreamSynchronize(s));
+                    if (n_tiny > tiny.cap)
+                        continue;   // too many coarse products for the list: the owner kernel redoes the heavy rows
+                    if (n_tiny)
+                        CSRK_LAUNCH(k_fix_tiny, (unsigned)div_up((int64_t)n_tiny, 256), 256, 0, s, tiny.buf, n_tiny, A, ea.as<int>(),
+                                    ebp, eb_u, (const void *)crp, 1, out->ci, cvs);
+                    out->stat_tiny = (int64_t)n_tiny;
                     out->stat_path = 2;
                 } else {
                     if (own_nw == 8) {
@@ -1708,6 +1888,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                 CSRK_LAUNCH(k, (unsigned)grid, DENSE_THREADS, 0, s, A, B, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                             gacc.as<double>(), gbm2.as<unsigned>(), (int)n, win, wc, kp, ks);
             }
+            break;
         }
         return CSRK_OK;
     };

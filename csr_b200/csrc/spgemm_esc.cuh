@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(256) k_esc_reduce_warp(const int32_t *__restri
 // columns) is left untouched and flagged: k_esc_reduce below takes it.
 constexpr int ESC_BUCKET_MAX = 32;
 constexpr int ESC_BPP = 2;   // buckets per product of capacity
+constexpr size_t esc_smem(int cap) { return (size_t)cap * (12 + 2 * ESC_BPP) + 16; }   // staging + 16-bit counters
 
 template <int THREADS, int PER, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *__restrict__ plist, int nbin,
@@ -800,21 +801,21 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     // bucket sort + merge, then the hash kernel for what it flagged (usually nothing: its CTAs only read the flags)
     if (cnt[2]) {
         auto k = k_esc_sortmerge<128, 4, 8>;
-        CSRK_LAUNCH(k, (unsigned)std::min(cnt[2], sms * 32), 128, 512 * 20 + 16, s, PL + off[2], cnt[2], po, ec, ev, pz, fl, af);
+        CSRK_LAUNCH(k, (unsigned)std::min(cnt[2], sms * 32), 128, esc_smem(512), s, PL + off[2], cnt[2], po, ec, ev, pz, fl, af);
         auto h = k_esc_reduce<1024, 128, 512>;
         CSRK_LAUNCH(h, (unsigned)std::min(cnt[2], sms * 8), 128, 1024 * 12 + 512 * 4, s, PL + off[2], cnt[2], po, ec, ev, pz, fl, af);
     }
     if (cnt[3]) {
         auto k = k_esc_sortmerge<256, 8, 5>;
-        CSRK_LAUNCH(k, (unsigned)std::min(cnt[3], sms * 16), 256, 2048 * 20 + 16, s, PL + off[3], cnt[3], po, ec, ev, pz, fl, af);
+        CSRK_LAUNCH(k, (unsigned)std::min(cnt[3], sms * 16), 256, esc_smem(2048), s, PL + off[3], cnt[3], po, ec, ev, pz, fl, af);
         auto h = k_esc_reduce<4096, 256, 2048>;
         CSRK_TRY(optin_smem(h, 4096 * 12 + 2048 * 4));
         CSRK_LAUNCH(h, (unsigned)std::min(cnt[3], sms * 4), 256, 4096 * 12 + 2048 * 4, s, PL + off[3], cnt[3], po, ec, ev, pz, fl, af);
     }
     if (cnt[4]) {
         auto k = k_esc_sortmerge<512, 16, 1>;
-        CSRK_TRY(optin_smem(k, 8192 * 20 + 16));
-        CSRK_LAUNCH(k, (unsigned)std::min(cnt[4], sms), 512, 8192 * 20 + 16, s, PL + off[4], cnt[4], po, ec, ev, pz, fl, af);
+        CSRK_TRY(optin_smem(k, esc_smem(8192)));
+        CSRK_LAUNCH(k, (unsigned)std::min(cnt[4], sms), 512, esc_smem(8192), s, PL + off[4], cnt[4], po, ec, ev, pz, fl, af);
         auto h = k_esc_reduce<16384, 512, 4096>;
         CSRK_TRY(optin_smem(h, 16384 * 12 + 4096 * 4));
         CSRK_LAUNCH(h, (unsigned)std::min(cnt[4], sms), 512, 16384 * 12 + 4096 * 4, s, PL + off[4], cnt[4], po, ec, ev, pz, fl, af);

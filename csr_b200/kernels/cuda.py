@@ -266,7 +266,9 @@ def spgemm_stats(h: cuda_h) -> dict:
     N.check(N.lib().csrk_spgemm_stats(_live(h), C.byref(p), C.byref(z)), "spgemm_stats")
     path = C.c_int()
     N.check(N.lib().csrk_spgemm_path(_live(h), C.byref(path)), "spgemm_path")
-    return {"products": p.value, "out_nnz": z.value,
+    side = C.c_int64()
+    N.check(N.lib().csrk_spgemm_side_list(_live(h), C.byref(side)), "spgemm_side_list")
+    return {"products": p.value, "out_nnz": z.value, "side_list": side.value,
             "dense_path": {0: "none", 1: "owner", 2: "fixed"}.get(path.value, str(path.value))}
 
 

@@ -75,7 +75,13 @@ int csrk_synchronize(void);
  *               different CTAs and summed in chunk order (0 = 1/8 of an SM's fair share, < 0 = never:
  *               every output element is then summed in the reference's own order, bit-identical values);
  * "radix_bits"  0 | 8 | 9 digit width of the stable sort behind transpose/order_columns
- *               (0 picks 9 when that saves a pass). */
+ *               (0 picks 9 when that saves a pass);
+ * "fix_tiny_cap" > 0: capacity (entries) of the fixed-point kernel's side list (0 = 1/32 of the products; when it
+ *               overflows the owner-computes kernel redoes the heavy rows);
+ * "spgemm_esc"  SpGEMM expand/sort/compress path: 0 off | 1 for wide results (more than four shared-memory column
+ *               windows: ncols > 106 496) | 2 always; "esc_target" 16..4096 products per pseudo-row (row x column
+ *               range) of that path; "esc_budget" > 0 caps the bytes of its expansion (default: half of the free
+ *               device memory; over budget the path declines and the per-row kernels run). */
 int csrk_set_option(const char *name, int64_t value);
 /* the library's own (non-blocking) stream, as a cudaStream_t */
 int csrk_get_stream(void **stream);
@@ -148,10 +154,13 @@ int csrk_spgemm_abt(csrk_h a, csrk_h b, csrk_h *c);
 int csrk_spgemm_stats(csrk_h c, int64_t *products, int64_t *out_nnz);
 /* Which numeric kernel handled the heavy (dense-accumulator) rows of the product that made c:
  * 0 none / the general dense kernels, 1 owner-computes (float64, reference summation order),
- * 2 64-bit fixed point on native shared-memory atomics (order-independent, only taken when all values
- * are finite and non-negative and max|a*b|/min|a*b| <= 2^(26 - ceil(log2(longest row + 1))), which keeps
- * every output element within 2^-35 of the exact sum; "spgemm_fixed" = 0 disables it). */
+ * 2 64-bit fixed point on native shared-memory atomics over power-of-two equilibrated operands (taken for
+ * finite values with exponents within +-400; products too small for the accumulator's grid go, exactly, through a
+ * side list and are added in float64, so every output element is within 2^-35 of sum_k |a_ik||b_kj|;
+ * "spgemm_fixed" = 0 disables it). */
 int csrk_spgemm_path(csrk_h c, int *path);
+/* how many products of that multiplication went through the fixed-point kernel's side list */
+int csrk_spgemm_side_list(csrk_h c, int64_t *entries);
 
 /* ---- transpose: csr/structure.py:172-247 ---------------------------------
  * Stable CSR->CSC.  rowptr dtype follows the input; values become float64

@@ -393,25 +393,60 @@ def test_fixed_point_signed_values(kernel):
     assert st2["dense_path"] == "fixed" and np.array_equal(chunked.values[heavy], got.values[heavy])
 
 
-@pytest.mark.parametrize("case", ["wide_range", "nonfinite", "centred"])
-def test_fixed_point_gate_falls_back_to_owner(kernel, case):
-    """The fixed-point kernel is only taken when its error bound holds: a wide dynamic range (mean-centred ratings
-    have values arbitrarily close to zero) or a non-finite value send the heavy rows to the owner-computes
-    kernel (bit-identical to the oracle)."""
+def _ratings_variant(case):
     R = synth.powerlaw_csr(16000, 12000, 1_600_000, seed=81, dtype="f8", alpha=0.5, cap=600, min_len=20, col_skew=2.0)
     v = R.values.copy()
-    if case == "centred":
-        lens = np.diff(R.rowptrs)
-        means = np.add.reduceat(v, R.rowptrs[:-1].astype(np.int64)) / np.maximum(lens, 1)
-        v = v - np.repeat(means, lens)
+    lens = np.diff(R.rowptrs)
+    rows = R.rowptrs[:-1].astype(np.int64)
+    if case == "centred":          # normalize_rows('center'): values arbitrarily close to 0, mixed signs
+        v = v - np.repeat(np.add.reduceat(v, rows) / np.maximum(lens, 1), lens)
+    elif case == "unit":           # normalize_rows('unit'): magnitudes differ by the rows' norms
+        v = v / np.repeat(np.sqrt(np.add.reduceat(v * v, rows)), lens)
     elif case == "wide_range":
+        v[::200] *= 1e-7
+    elif case == "very_wide_range":
         v[::5] *= 1e-7
-    else:
+    elif case == "nonfinite":
         v[12345] = np.inf
-    M = CSR(R.nrows, R.ncols, R.nnz, R.rowptrs, R.colinds, v).transpose()
+    return CSR(R.nrows, R.ncols, R.nnz, R.rowptrs, R.colinds, v).transpose()
+
+
+@pytest.mark.parametrize("case", ["centred", "unit", "wide_range"])
+def test_fixed_point_any_value_range(kernel, case):
+    """Round 2: the operands are equilibrated by exact powers of two (A by row, B by column) and products below
+    the accumulator's grid go through an exact side list, so mean-centred and unit-normalised ratings -- the
+    inputs of item-item similarity -- and any other finite values take the fixed-point kernel, with every element
+    within 1e-10 of sum_k |a_ik||b_kj| (no absolute term)."""
+    M = _ratings_variant(case)
     ref = orc.mult_abt(M, M)
     rp, ci, vs = canonical(ref)
-    got, st = _abt(kernel, M, own_chunk_prod=-1)
+    terms = spgemm_terms(M, M, transpose=True)
+    got, st = _abt(kernel, M)
+    assert st["dense_path"] == "fixed"
+    assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
+    assert_values_close(got.values, vs, 1e-10, terms)
+    if case == "wide_range":
+        assert st["side_list"] > 0
+    if case == "unit":
+        assert st["side_list"] == 0   # equilibration alone brings the products within the accumulator's range
+    chunked, st2 = _abt(kernel, M, own_chunk_prod=30000)
+    assert st2["dense_path"] == "fixed"
+    assert_values_close(chunked.values, vs, 1e-10, terms)
+
+
+@pytest.mark.parametrize("case", ["nonfinite", "side_list_overflow", "very_wide_range"])
+def test_fixed_point_gate_falls_back_to_owner(kernel, case):
+    """A non-finite value, or more coarse products than the side list holds, send the heavy rows to the
+    owner-computes kernel (bit-identical to the oracle)."""
+    # (a 64-entry list overflows at once; "very_wide_range" -- a third of the products below the grid -- overflows
+    # the default one: 1/32 of the products)
+    M = _ratings_variant({"side_list_overflow": "wide_range"}.get(case, case))
+    ref = orc.mult_abt(M, M)
+    rp, ci, vs = canonical(ref)
+    try:
+        got, st = _abt(kernel, M, own_chunk_prod=-1, **({"fix_tiny_cap": 64} if case == "side_list_overflow" else {}))
+    finally:
+        kernel.set_option("fix_tiny_cap", 0)
     assert st["dense_path"] == "owner"
     assert np.array_equal(got.rowptrs, rp) and np.array_equal(got.colinds, ci)
     heavy = np.repeat(np.diff(rp) > 8192, np.diff(rp))

@@ -1,12 +1,14 @@
 """
-CPU: a numpy model of the SpGEMM fixed-point accumulator (csrc/spgemm.cu, k_num_fixed and the gate in
-spgemm_run), checking the error bound the gate promises.
+CPU: a numpy model of the SpGEMM fixed-point accumulator (csrc/spgemm.cu: k_num_fixed, k_fix_tiny and the
+equilibration in spgemm_run), checking the error bound it promises.
 
-Model: a row with `length` stored entries gets hb = ceil(log2(length + 1)) bits of headroom; with
-2^x >= max|a*b| (frexp) every product is rounded once to a multiple of 2^-(62 - x - hb) and the integers
-are added exactly (two 32-bit words with a carry on the device, Python ints here).  The gate admits
-non-negative finite values with max|a*b| / min|a*b| <= 2^(26 - hb); the claim is a relative error of at
-most 2^-35 for EVERY output element, whatever the number of terms (up to `length`) and their order.
+Model (round 2): the operands are equilibrated by exact powers of two -- a_ik * 2^-ea_i with
+max_k |a_ik| < 2^ea_i, b_kj * 2^-eb_j with max_k |b_kj| < 2^eb_j -- so every product is below 1 in magnitude.
+A row with `length` stored entries gets hb = ceil(log2(length + 1)) bits of headroom and accumulates
+T = rint(p' * 2^(62 - hb)) as exact integers (two 32-bit words with a carry on the device, Python ints
+here); a product with |T| < 2^35 is NOT accumulated but added exactly, in float64, to the finished element
+(the side list).  The claim: EVERY output element is within 2^-35 of sum |terms|, whatever the values, the
+number of terms (up to `length`) and their order.
 """
 
 import math
@@ -15,52 +17,57 @@ import numpy as np
 import pytest
 
 
-def fixed_point_sum(terms, length, pmax):
+def fixed_point_sum(terms, length):
+    """terms: equilibrated products (|p'| < 1) of ONE output element of a row with `length` entries."""
     hb = int(length).bit_length()                 # ceil(log2(length + 1)), as headroom_bits()
-    _, x = math.frexp(pmax)                       # pmax <= 2^x
-    sh = 62 - x - hb
-    scaled = np.rint(np.ldexp(terms, sh))         # __double2ll_rn(p * 2^sh): exact scaling, one rounding
-    assert np.all(np.abs(scaled) < 2.0 ** 62)
-    total = sum(int(v) for v in scaled)           # exact integer addition (order-independent)
+    sh = 62 - hb
+    scaled = np.rint(np.ldexp(terms, sh))         # __double2ll_rn(p' * 2^sh): exact scaling, one rounding
+    big = np.abs(scaled) >= 2.0 ** 35
+    total = sum(int(v) for v in scaled[big])      # exact integer addition (order-independent)
     assert abs(total) < 2 ** 63                   # fits the 64-bit accumulator
-    return math.ldexp(float(total), -sh), hb      # (double)v * 2^-sh
+    out = math.ldexp(float(total), -sh)           # (double)v * 2^-sh
+    for t in terms[~big]:                         # k_fix_tiny: float64 atomicAdd, one at a time
+        out += float(t)
+    return out, int((~big).sum())
 
 
 @pytest.mark.parametrize("length", [9000, 100000, 1 << 20])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_error_bound_at_the_gate_limit(length, seed):
+def test_error_bound_for_any_value_range(length, seed):
     rng = np.random.default_rng(seed)
-    hb = int(length).bit_length()
-    ratio = 2.0 ** (26 - hb)                      # the widest value range the gate admits for this row length
-    pmax = 10.0 ** rng.uniform(-30, 30)
-    pmin = pmax / ratio
-    for nterms in (1, 2, 17, length):             # one output element may collect up to `length` products
-        # worst case for a relative bound: all terms at the small end, plus the extremes
-        for terms in (np.full(nterms, pmin), rng.uniform(pmin, pmax, nterms),
-                      np.concatenate([[pmax], np.full(nterms - 1, pmin)])):
-            got, _ = fixed_point_sum(terms, length, pmax)
+    for nterms in (1, 2, 17, 4096):               # one output element may collect up to `length` products
+        for terms in (np.full(nterms, 1.0 - 2.0 ** -20),                         # all at the top: needs the headroom
+                      rng.uniform(-1, 1, nterms) * 10.0 ** rng.uniform(-12, 0, nterms),   # twelve decades, mixed signs
+                      np.full(nterms, 1.37e-9),                                   # all below the grid: side list only
+                      np.concatenate([[0.9], np.full(nterms - 1, -3.1e-11)])):
+            got, _ = fixed_point_sum(np.asarray(terms, np.float64), length)
             exact = math.fsum(terms)
-            assert abs(got - exact) <= 2.0 ** -35 * exact, (length, nterms, got, exact)
+            assert abs(got - exact) <= 2.0 ** -35 * math.fsum(np.abs(terms)), (length, nterms, got, exact)
+
+
+def test_headroom_is_enough_for_a_full_row():
+    length = 100000
+    got, small = fixed_point_sum(np.full(length, 1.0 - 2.0 ** -30), length)
+    assert small == 0 and abs(got - length * (1.0 - 2.0 ** -30)) <= 2.0 ** -35 * length
 
 
 def test_order_independence_and_chunking():
     rng = np.random.default_rng(7)
-    terms = rng.uniform(0.25, 25.0, 50000)        # products of ratings in [0.5, 5]
-    a, _ = fixed_point_sum(terms, 60000, 25.0)
-    b, _ = fixed_point_sum(rng.permutation(terms), 60000, 25.0)
+    terms = rng.uniform(0.01, 1.0, 50000)         # equilibrated products of ratings
+    a, _ = fixed_point_sum(terms, 60000)
+    b, _ = fixed_point_sum(rng.permutation(terms), 60000)
     # chunks: integer partial sums added afterwards give the same integer
-    hb = (60000).bit_length()
-    sh = 62 - math.frexp(25.0)[1] - hb
+    sh = 62 - (60000).bit_length()
     parts = [sum(int(v) for v in np.rint(np.ldexp(c, sh))) for c in np.array_split(terms, 7)]
     c = math.ldexp(float(sum(parts)), -sh)
     assert a == b == c
 
 
-def test_gate_rejects_what_the_bound_cannot_cover():
-    # one decade more dynamic range than admitted: the bound is no longer guaranteed (and is in fact broken)
+def test_the_side_list_is_what_keeps_small_terms():
+    # without it a product below the grid would simply vanish: the bound would be broken
     length = 100000
-    hb = int(length).bit_length()
-    pmax = 1.0
-    pmin = pmax / (2.0 ** (26 - hb) * 2.0 ** 12)
-    got, _ = fixed_point_sum(np.array([pmin * 1.37]), length, pmax)
-    assert abs(got - pmin * 1.37) > 2.0 ** -35 * pmin * 1.37
+    sh = 62 - int(length).bit_length()
+    p = 1.37 * 2.0 ** -(sh + 2)
+    assert np.rint(np.ldexp(p, sh)) == 0.0
+    got, small = fixed_point_sum(np.array([p]), length)
+    assert small == 1 and got == p
