@@ -1034,6 +1034,29 @@ __global__ void __launch_bounds__(256) k_col_expo(MatView B, int *__restrict__ e
             atomicMax(&eb[B.ci[k]], (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1022);
     }
 }
+// bit patterns of the smallest non-zero and the largest finite |v| (mm[0], mm[1]): a narrow range lets the
+// fixed-point kernel run without its side-list test
+__global__ void __launch_bounds__(256) k_val_range(const void *__restrict__ vs, int vk, int64_t nnz, unsigned long long *__restrict__ mm)
+{
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = fabs(ld_val(vs, vk, i));
+        if (v != 0.0) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+            lo = min(lo, b);
+            hi = max(hi, b);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && hi) {
+        atomicMin(&mm[0], lo);
+        atomicMax(&mm[1], hi);
+    }
+}
 __global__ void __launch_bounds__(256) k_fill_i32(int *__restrict__ p, int64_t n, int v)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1117,7 +1140,9 @@ __device__ __forceinline__ int headroom_bits(int64_t len)
 
 constexpr int FIX_MAX_PASSES = 4;
 
-template <int THREADS>
+// SIDE = false: the caller has checked that no product can fall below the grid (max|a*b| / min|a*b| <= 2^(25-hb)):
+// the side-list test is compiled out
+template <int THREADS, bool SIDE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, const int64_t *__restrict__ c_rp,
             int32_t *__restrict__ c_ci, double *__restrict__ c_vs, int both_f32, int n_cols, int win, int passes,
@@ -1244,17 +1269,19 @@ k_num_fixed(MatView A, MatView B, const int32_t *__restrict__ rows, int nbin, co
                             const double pr = both_f32 ? (double)__fmul_rn((float)pav, (float)val[u]) * scale_f
                                                        : __dmul_rn(pav, val[u]);
                             const long long T = __double2ll_rn(pr);
-                            const bool big = fabs(pr) >= 34359738368.0;   // 2^35: |T| >= 2^35, rounding error <= 2^-36 |term|
-                            val[u] = pr;
-                            small |= (unsigned)(!big && pr != 0.0) << u;
-                            if (big) {   // (kept this short: two predicated atomics, the four chains overlap)
+                            const bool big = !SIDE || fabs(pr) >= 34359738368.0;   // 2^35: rounding error <= 2^-36 |term|
+                            if (SIDE) {
+                                val[u] = pr;
+                                small |= (unsigned)(!big && pr != 0.0) << u;
+                            }
+                            if (SIDE ? big : col[u] >= 0) {   // (kept this short: two predicated atomics, the four chains overlap)
                                 const unsigned tlo = (unsigned)T, thi = (unsigned)((unsigned long long)T >> 32);
                                 const unsigned old = atomicAdd(&slo[col[u] - c0], tlo);
                                 atomicAdd(&shi[col[u] - c0], thi + ((old + tlo) < old ? 1u : 0u));
                             }
                         }
                         // rounded too coarsely for the accumulator: exact side list (rare; one vote per 128 entries)
-                        if (__any_sync(0xffffffffu, small != 0)) {
+                        if (SIDE && __any_sync(0xffffffffu, small != 0)) {
 #pragma unroll
                             for (int u = 0; u < 4; u++)
                                 tiny_append(tiny, (small >> u) & 1u, row, col[u], val[u], s_tbase, s_tused, tid >> 5, lane);
@@ -1703,7 +1730,7 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
             DevBuf ea, eb, bscaled, tiny_buf, tiny_cnt;
             TinyList tiny{nullptr, nullptr, 0};
             MatView Bs = B;   // B with its values equilibrated by column (fixed-point kernel)
-            bool eb_uniform = false;
+            bool eb_uniform = false, fix_side = true;
             int eb_u = 0;
             if (owner) {
                 // both dense kernels walk B's rows by column range: rows strictly increasing in column
@@ -1717,7 +1744,16 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                     hb++;  // ceil(log2(longest row + 1)): terms per output element
                 const bool want_fixed = attempt == 0 && options().spgemm_fixed.load() != 0 && hb <= 24 && passes <= FIX_MAX_PASSES;
                 int er[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};   // min / max exponent: A's rows, B's columns
+                unsigned long long vr[4] = {~0ull, 0ull, ~0ull, 0ull};       // smallest / largest |v| of A, of B (bits)
+                DevBuf vrange;
                 if (want_fixed) {
+                    CSRK_TRY(vrange.alloc(sizeof vr, s));
+                    CSRK_CUDA(cudaMemcpyAsync(vrange.p, vr, sizeof vr, cudaMemcpyHostToDevice, s));
+                    CSRK_LAUNCH(k_val_range, (unsigned)std::min<int64_t>(div_up(a->nnz, 256), (int64_t)sms * 8), 256, 0, s, a->vs,
+                                a->val_kind, a->nnz, vrange.as<unsigned long long>());
+                    CSRK_LAUNCH(k_val_range, (unsigned)std::min<int64_t>(div_up(b->nnz, 256), (int64_t)sms * 8), 256, 0, s, b->vs,
+                                b->val_kind, b->nnz, vrange.as<unsigned long long>() + 2);
+                    CSRK_CUDA(cudaMemcpyAsync(vr, vrange.p, sizeof vr, cudaMemcpyDeviceToHost, s));
                     CSRK_TRY(ea.alloc(sizeof(int) * (size_t)m, s));
                     CSRK_TRY(eb.alloc(sizeof(int) * (size_t)n, s));
                     CSRK_TRY(erange.alloc(sizeof er, s));
@@ -1747,6 +1783,11 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                     tiny.cap = opt_cap > 0 ? (unsigned long long)opt_cap : cap;
                     eb_uniform = er[2] == er[3];   // every column of B peaks at the same exponent: no scaled copy
                     eb_u = er[2];
+                    if (vr[1] && vr[3]) {   // products spanning at most 2^(25-hb): none can fall below the grid
+                        double lim[4];
+                        memcpy(lim, vr, sizeof lim);
+                        fix_side = !(lim[1] * lim[3] <= ldexp(lim[0] * lim[2], 25 - hb));
+                    }
                     if ((eb_uniform || bscaled.alloc((size_t)b->nnz * bvk, s) == CSRK_OK) &&
                         tiny_buf.alloc_owned(sizeof(TinyEnt) * (size_t)tiny.cap, s) == CSRK_OK &&
                         tiny_cnt.alloc_zero(sizeof(unsigned long long), s) == CSRK_OK) {
@@ -1814,20 +1855,23 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
                     const int *ebp = eb_uniform ? nullptr : eb.as<int>();
                     const int64_t ft = options().fix_threads.load();
                     if (ft == 1024) {
-                        auto k = k_num_fixed<1024>;
-                        CSRK_TRY(optin_smem(k, bytes));
+                        auto k = fix_side ? k_num_fixed<1024, true> : k_num_fixed<1024, false>;
+                        CSRK_TRY(optin_smem(k_num_fixed<1024, true>, bytes));
+                        CSRK_TRY(optin_smem(k_num_fixed<1024, false>, bytes));
                         CSRK_LAUNCH(k, (unsigned)grid, 1024, bytes, s, A, Bs, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                                     (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
                                     chunk_base.as<int>(), nitems, partial.as<long long>(), ea.as<int>(), ebp, eb_u, tiny);
                     } else if (ft == 768) {
-                        auto k = k_num_fixed<768>;
-                        CSRK_TRY(optin_smem(k, bytes));
+                        auto k = fix_side ? k_num_fixed<768, true> : k_num_fixed<768, false>;
+                        CSRK_TRY(optin_smem(k_num_fixed<768, true>, bytes));
+                        CSRK_TRY(optin_smem(k_num_fixed<768, false>, bytes));
                         CSRK_LAUNCH(k, (unsigned)grid, 768, bytes, s, A, Bs, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                                     (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
                                     chunk_base.as<int>(), nitems, partial.as<long long>(), ea.as<int>(), ebp, eb_u, tiny);
                     } else {
-                        auto k = k_num_fixed<512>;
-                        CSRK_TRY(optin_smem(k, bytes));
+                        auto k = fix_side ? k_num_fixed<512, true> : k_num_fixed<512, false>;
+                        CSRK_TRY(optin_smem(k_num_fixed<512, true>, bytes));
+                        CSRK_TRY(optin_smem(k_num_fixed<512, false>, bytes));
                         CSRK_LAUNCH(k, (unsigned)grid, 512, bytes, s, A, Bs, NL + noff[5], ncnt[5], crp, out->ci, cvs, both_f32,
                                     (int)n, win, passes, wc, kp, ks, split.as<int32_t>(), item_off.as<int>(),
                                     chunk_base.as<int>(), nitems, partial.as<long long>(), ea.as<int>(), ebp, eb_u, tiny);
