@@ -146,6 +146,7 @@ struct Options {
     std::atomic<int64_t> fix_tiny_cap{0};               // > 0: capacity (entries) of the fixed-point kernel's side list (tests force an overflow)
     std::atomic<int64_t> spgemm_esc{1};                 // SpGEMM expand/sort/compress path: 0 off, 1 for wide results, 2 always (tests)
     std::atomic<int64_t> esc_target{1536};              // products per pseudo-row (row x column range) of that path
+    std::atomic<int64_t> esc_stride{1};                 // its walk kernels take work items a prime stride apart (0: in order)
     std::atomic<int64_t> esc_budget{0};                 // > 0: cap in bytes on its expansion (else: half of the free memory)
     std::atomic<int64_t> own_nw{16};                    // warps (column ranges) per CTA in the owner-computes SpGEMM
 };

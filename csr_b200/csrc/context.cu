@@ -416,6 +416,8 @@ int csrk_set_option(const char *name, int64_t value)
     } else if (!strcmp(name, "esc_target")) {
         CSRK_ARG(value >= 16 && value <= 4096, "esc_target must be in 16..4096");
         options().esc_target = value;
+    } else if (!strcmp(name, "esc_stride")) {
+        options().esc_stride = value ? 1 : 0;
     } else if (!strcmp(name, "esc_budget")) {
         CSRK_ARG(value >= 0, "esc_budget is a byte count (0 = what the device has free)");
         options().esc_budget = value;

@@ -171,10 +171,14 @@ struct EscItem {
     int64_t as, ae;   // A entries of this item
 };
 __device__ __forceinline__ EscItem esc_item(const MatView &A, const int32_t *__restrict__ rows, int n,
-                                            const int *__restrict__ item_off, int *s_idx)
+                                            const int *__restrict__ item_off, int *s_idx, unsigned stride)
 {
+    // stride > 1 (count kernel): consecutive CTAs take items `stride` apart (coprime to the item count), so that the
+    // items of one heavy row, which all add to the same pseudo-row counters, are spread over the kernel's lifetime
+    // (21 -> 17 ms at configs[3]).  The scatter kernel keeps them together (stride 1): their partial-sector writes
+    // into the same segments then merge in L2 (41 ms; 68 ms when spread)
+    const int item = (int)(((uint64_t)blockIdx.x * stride) % gridDim.x);
     if (threadIdx.x == 0) {
-        const int item = blockIdx.x;
         int lo = 0, hi = n;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -190,17 +194,17 @@ __device__ __forceinline__ EscItem esc_item(const MatView &A, const int32_t *__r
     it.idx = *s_idx;
     const int32_t row = rows[it.idx];
     const int64_t as = ld_rp(A.rp, A.rp64, row), ae = ld_rp(A.rp, A.rp64, (int64_t)row + 1);
-    it.as = as + (int64_t)(blockIdx.x - item_off[it.idx]) * ESC_ITEM;
+    it.as = as + (int64_t)(item - item_off[it.idx]) * ESC_ITEM;
     it.ae = min(ae, it.as + ESC_ITEM);
     return it;
 }
 
 __global__ void __launch_bounds__(ESC_WALK_THREADS)
 k_esc_count(MatView A, MatView B, const int32_t *__restrict__ rows, int n, const int *__restrict__ item_off,
-            const int *__restrict__ pbase, unsigned *__restrict__ pcount)
+            const int *__restrict__ pbase, unsigned *__restrict__ pcount, unsigned stride)
 {
     __shared__ int s_idx;
-    const EscItem it = esc_item(A, rows, n, item_off, &s_idx);
+    const EscItem it = esc_item(A, rows, n, item_off, &s_idx, stride);
     const int pb = pbase[it.idx];
     const uint64_t scale = ((uint64_t)(pbase[it.idx + 1] - pb) << 32) / (uint64_t)B.ncols;
     unsigned *cnt = pcount + pb;
@@ -242,10 +246,11 @@ __global__ void __launch_bounds__(256) k_esc_badlist(const int32_t *__restrict__
 __global__ void __launch_bounds__(ESC_WALK_THREADS)
 k_esc_scatter(MatView A, MatView B, const int32_t *__restrict__ rows, int n, const int *__restrict__ item_off,
               const int *__restrict__ pbase, const int *__restrict__ bad, const int64_t *__restrict__ poff,
-              unsigned *__restrict__ pcur, int32_t *__restrict__ ecol, double *__restrict__ eval, int both_f32)
+              unsigned *__restrict__ pcur, int32_t *__restrict__ ecol, double *__restrict__ eval, int both_f32,
+              unsigned stride)
 {
     __shared__ int s_idx;
-    const EscItem it = esc_item(A, rows, n, item_off, &s_idx);
+    const EscItem it = esc_item(A, rows, n, item_off, &s_idx, stride);
     if (bad[it.idx])
         return;
     const int pb = pbase[it.idx];
@@ -737,8 +742,15 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     CSRK_TRY(st.old_list.alloc(sizeof(int32_t) * (size_t)n, s));
     CSRK_TRY(n_old_d.alloc_zero(sizeof(int), s));
     CSRK_LAUNCH(k_esc_prow, (unsigned)div_up((int64_t)n * 32, 256), 256, 0, s, st.pbase.as<int>(), n, st.prow.as<int32_t>());
+    unsigned stride = 1;
+    if (options().esc_stride.load())
+        for (unsigned c : {7919u, 7907u, 7901u, 7883u, 7879u})   // a prime that does not divide the item count
+            if ((unsigned)nitems % c) {
+                stride = c;
+                break;
+            }
     CSRK_LAUNCH(k_esc_count, (unsigned)nitems, ESC_WALK_THREADS, 0, s, A, B, rows, n, item_off.as<int>(), st.pbase.as<int>(),
-                pcount.as<unsigned>());
+                pcount.as<unsigned>(), stride);
     const unsigned pgrid = (unsigned)div_up(np, 256);
     CSRK_LAUNCH(k_esc_check, pgrid, 256, 0, s, pcount.as<unsigned>(), st.prow.as<int32_t>(), np, st.bad.as<int>());
     CSRK_LAUNCH(k_esc_mask, pgrid, 256, 0, s, pcount.as<unsigned>(), st.prow.as<int32_t>(), np, st.bad.as<int>());
@@ -779,7 +791,7 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     CSRK_TRY(pcur.alloc_zero(sizeof(unsigned) * (size_t)np, s));
     CSRK_LAUNCH(k_esc_scatter, (unsigned)nitems, ESC_WALK_THREADS, 0, s, A, B, rows, n, item_off.as<int>(), st.pbase.as<int>(),
                 st.bad.as<int>(), st.poff.as<int64_t>(), pcur.as<unsigned>(), st.ecol.as<int32_t>(), st.eval.as<double>(),
-                both_f32);
+                both_f32, 1u);
     CSRK_TRACE_MARK("spgemm esc: scatter", s);
     // pseudo-rows by size
     BinSpec spec{{0, 64, 512, 2048, ESC_CAP, INT64_MAX}};

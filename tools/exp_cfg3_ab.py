@@ -8,6 +8,8 @@ K = get_kernel("cuda")
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 frac = float(sys.argv[2]) if len(sys.argv) > 2 else 0.079
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+for kv in sys.argv[4:]:
+    k, v = kv.split('='); K.set_option(k, int(v)); print('option', k, v)
 t = time.perf_counter(); A = synth.cfg4_square(scale); print("gen", A, f"{time.perf_counter()-t:.1f}s", flush=True)
 ah = K.to_handle(A)
 rows = int(A.nrows * frac)
