@@ -8,8 +8,11 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 
 #include "common.cuh"
+
+static void (*g_out_pool_release)() = nullptr;   // set once csrk_export has created its pinned slots
 
 namespace csrk {
 
@@ -343,6 +346,8 @@ int csrk_shutdown(void)
     CSRK_CUDA(cudaSetDevice(c.device));
     CSRK_CUDA(cudaStreamSynchronize(c.stream));
     ws_release_all();
+    if (g_out_pool_release)
+        g_out_pool_release();
     CSRK_CUDA(cudaStreamDestroy(c.stream));
     c.stream = nullptr;
     c.inited = false;
@@ -533,6 +538,101 @@ int csrk_dims(csrk_h h, int32_t *nrows, int32_t *ncols, int64_t *nnz, int *rp_is
     return CSRK_OK;
 }
 
+// Large device -> PAGEABLE host copies.  cudaMemcpy into pageable memory runs at ~4 GB/s (the driver stages through
+// its own buffer and one thread takes the page faults of a freshly allocated destination): the 19.6 GB result of
+// configs[2] took 4.9 s to reach its NumPy arrays.  Here a few host threads each own a pinned slot and a stream: DMA
+// a chunk into the slot, copy it into place, next chunk -- while some threads copy (and fault pages in) the
+// others' DMAs run.  Pinned destinations and small copies take the plain path.
+namespace {
+constexpr size_t OUT_SLOT = (size_t)16 << 20;
+constexpr int OUT_THREADS = 8;
+struct OutPoolState {
+    char *pin = nullptr;
+    cudaStream_t st[OUT_THREADS] = {};
+    bool ok = false, tried = false;
+};
+struct OutPool : OutPoolState {
+    std::mutex mu;
+    OutPool &operator=(const OutPoolState &o)
+    {
+        static_cast<OutPoolState &>(*this) = o;
+        return *this;
+    }
+};
+OutPool &out_pool()
+{
+    static OutPool p;
+    return p;
+}
+}  // namespace
+
+static void out_pool_release()
+{
+    OutPool &P = out_pool();
+    std::lock_guard<std::mutex> g(P.mu);
+    if (P.pin)
+        (void)cudaFreeHost(P.pin);
+    for (int k = 0; k < OUT_THREADS; k++)
+        if (P.st[k])
+            (void)cudaStreamDestroy(P.st[k]);
+    P = OutPoolState();
+}
+
+static int copy_to_host(void *dst, const void *src, size_t bytes, cudaStream_t s)
+{
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    OutPool &P = out_pool();
+    if (pinned || bytes < 8 * OUT_SLOT) {
+        CSRK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        return CSRK_OK;
+    }
+    std::lock_guard<std::mutex> g(P.mu);
+    if (!P.tried) {
+        P.tried = true;
+        g_out_pool_release = out_pool_release;
+        P.ok = cudaHostAlloc((void **)&P.pin, OUT_SLOT * OUT_THREADS, cudaHostAllocDefault) == cudaSuccess;
+        for (int k = 0; P.ok && k < OUT_THREADS; k++)
+            P.ok = cudaStreamCreateWithFlags(&P.st[k], cudaStreamNonBlocking) == cudaSuccess;
+        (void)cudaGetLastError();
+    }
+    if (!P.ok) {
+        CSRK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        return CSRK_OK;
+    }
+    CSRK_CUDA(cudaStreamSynchronize(s));   // what is copied has been produced on the library stream
+    const size_t nchunk = (bytes + OUT_SLOT - 1) / OUT_SLOT;
+    std::atomic<int> failed{0};
+    const int device = ctx().device;
+    auto work = [&](int k) {
+        if (cudaSetDevice(device) != cudaSuccess) {
+            failed = 1;
+            return;
+        }
+        char *slot = P.pin + (size_t)k * OUT_SLOT;
+        for (size_t c = (size_t)k; c < nchunk && !failed; c += OUT_THREADS) {
+            const size_t off = c * OUT_SLOT, n = std::min(OUT_SLOT, bytes - off);
+            if (cudaMemcpyAsync(slot, (const char *)src + off, n, cudaMemcpyDeviceToHost, P.st[k]) != cudaSuccess ||
+                cudaStreamSynchronize(P.st[k]) != cudaSuccess) {
+                failed = 1;
+                return;
+            }
+            memcpy((char *)dst + off, slot, n);
+        }
+    };
+    std::thread th[OUT_THREADS];
+    for (int k = 0; k < OUT_THREADS; k++)
+        th[k] = std::thread(work, k);
+    for (int k = 0; k < OUT_THREADS; k++)
+        th[k].join();
+    if (failed) {
+        set_error("device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return CSRK_ECUDA;
+    }
+    return CSRK_OK;
+}
+
 int csrk_export(csrk_h h, void *rowptrs, int32_t *colinds, void *values)
 {
     CSRK_ARG(h != nullptr, "NULL handle");
@@ -542,10 +642,10 @@ int csrk_export(csrk_h h, void *rowptrs, int32_t *colinds, void *values)
     CSRK_CUDA(cudaMemcpyAsync(rowptrs, h->rp, ((size_t)h->nrows + 1) * (h->rp_is64 ? 8 : 4), cudaMemcpyDeviceToHost, s));
     if (h->nnz) {
         CSRK_ARG(colinds != nullptr, "colinds is NULL");
-        CSRK_CUDA(cudaMemcpyAsync(colinds, h->ci, (size_t)h->nnz * 4, cudaMemcpyDeviceToHost, s));
+        CSRK_TRY(copy_to_host(colinds, h->ci, (size_t)h->nnz * 4, s));
         if (h->val_kind) {
             CSRK_ARG(values != nullptr, "values is NULL");
-            CSRK_CUDA(cudaMemcpyAsync(values, h->vs, (size_t)h->nnz * h->val_kind, cudaMemcpyDeviceToHost, s));
+            CSRK_TRY(copy_to_host(values, h->vs, (size_t)h->nnz * h->val_kind, s));
         }
     }
     CSRK_CUDA(cudaStreamSynchronize(s));

@@ -520,6 +520,25 @@ def test_keep_resident_handle_cache(kernel):
     assert key not in csr_mod._resident._live and not h2.H
 
 
+def test_large_export_goes_through_the_threaded_copy(kernel):
+    """Arrays above 128 MB leave the device through pinned slots filled and drained by several host threads
+    (context.cu copy_to_host): the round trip must be bit-exact, with a tail chunk that is not slot-sized."""
+    n = 36_000_001
+    rng = np.random.default_rng(91)
+    rp = np.zeros(1001, np.int64)
+    rp[1:] = np.sort(rng.integers(0, n, 1000))
+    rp[-1] = n
+    cols = rng.integers(0, 50_000, n).astype(np.int32)
+    vals = rng.standard_normal(n)
+    A = CSR(1000, 50_000, n, rp, cols, vals)
+    h = kernel.to_handle(A)
+    try:
+        B = kernel.from_handle(h)
+    finally:
+        kernel.release_handle(h)
+    assert np.array_equal(B.rowptrs, A.rowptrs) and np.array_equal(B.colinds, cols) and np.array_equal(B.values, vals)
+
+
 def test_released_handle_is_rejected(kernel):
     h = kernel.to_handle(CSR.empty(3, 3))
     kernel.release_handle(h)
