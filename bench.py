@@ -748,7 +748,25 @@ def bench_spgemm(args, env):
                         "traffic_source": traffic_src,
                         "note": "P/Z products per output entry go through shared-memory accumulators, so the "
                                 "algorithmic-bytes roofline is far from binding; products_per_s is the work rate"}}
+    res["side_list"] = int(st.get("side_list", 0))
     if rank == 0 and world == 1:
+        # ---- the inputs item-item similarity really sees: mean-centred and unit-normalised rows (the handle is
+        # normalised on the device, CSR.normalize_rows).  Timing only; parity of these value ranges is
+        # tests/test_cuda_large.py::test_fixed_point_any_value_range
+        res["normalised"] = {}
+        for kind in ("center", "unit"):
+            nh = K.to_handle(M)
+            K.normalize_rows(nh, kind)
+            K.release_handle(K.mult_abt(nh, nh))
+            K.synchronize()
+            t0 = time.perf_counter()
+            ch2 = K.mult_abt(nh, nh)
+            t_n = time.perf_counter() - t0
+            st2 = K.spgemm_stats(ch2)
+            K.release_handle(ch2)
+            K.release_handle(nh)
+            res["normalised"][kind] = {"ms": round(t_n * 1e3, 3), "dense_path": st2["dense_path"],
+                                       "side_list": int(st2.get("side_list", 0)), "out_nnz": int(st2["out_nnz"])}
         # ---- e2e: the CSR-level call with HOST arrays: upload, A*A^T, device-side zero filter, copy-out of C
         if not args.skip_spgemm_e2e:
             Mh = CSR(M.nrows, M.ncols, M.nnz, M.rowptrs, M.colinds, M.values)
@@ -759,7 +777,7 @@ def bench_spgemm(args, env):
             res["e2e"] = {"value": round(Z / t_e2e, 1), "unit": "nnz/s", "ms": round(t_e2e * 1e3, 1),
                           "h2d_bytes_per_step": int(2 * csr_bytes(M)), "d2h_bytes_per_step": int(Z * 12 + (M.nrows + 1) * 4),
                           "call": "csr_b200.CSR.multiply(M, transpose=True) with host arrays: two uploads, mult_abt, device "
-                                  "zero filter, copy-out of C into pageable NumPy arrays (one run)"}
+                                  "zero filter, copy-out of C into pageable NumPy arrays through pinned slots and host threads (one run)"}
             del C_host
         # ---- CPU: the reference kernel on a sample of A's rows, all cores
         arm = CpuArm()

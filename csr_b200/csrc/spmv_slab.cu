@@ -879,6 +879,9 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
     if (tid == 33)
         *reinterpret_cast<uint4 *>(sl_smem + (zpad + 16u - smem0)) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();   // the only CTA-wide barrier
+    // programmatic dependent launch: k_slab_fixup may be scheduled now (its CTAs fit beside this one and wait in
+    // griddepcontrol.wait until this grid has completed and its carries are visible): no launch gap after the kernel
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // CTA g walks the slabs starting at slab g*nslab/G and wraps around, so that at any moment the CTAs pull
     // different parts of x out of L2
     const int slab0 = (int)(((int64_t)blockIdx.x * a.nslab) / gridDim.x);
@@ -1023,12 +1026,15 @@ __global__ void __launch_bounds__(256)
 k_slab_fixup(const int32_t *__restrict__ split, int n_split, const double *__restrict__ carry, YOut y)
 {
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int32_t row = 0, q0 = 0, nq = 0;
+    if (k < n_split)   // (the plan's arrays do not depend on the slab kernel: fetched while it still runs)
+        row = split[3 * k], q0 = split[3 * k + 1], nq = split[3 * k + 2];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the slab kernel's carries (no-op without the launch attribute)
     if (k >= n_split)
         return;
-    const int32_t row = split[3 * k], q0 = split[3 * k + 1], nq = split[3 * k + 2];
     double tot = 0.0;
     for (int j = lane; j < nq; j += 32)
-        tot += carry[q0 + j];
+        tot += __ldcg(&carry[q0 + j]);   // written by the grid this one overlaps: from L2
     tot = warp_sum(tot);
     if (lane == 0)
         store_y<MULTI>(y, row, tot, true);
@@ -1044,8 +1050,24 @@ static int slab_launch(StreamPlan *P, const SlArgs &a, const void *d_x, const YO
         optin = ctx().smem_optin;
     }
     CSRK_LAUNCH(k, (unsigned)P->G, (unsigned)(P->NW + 1) * 32, P->smem_bytes, s, a, (const XT *)d_x, y, carry);
-    if (P->n_split)
-        CSRK_LAUNCH((k_slab_fixup<MULTI>), (unsigned)div_up((int64_t)P->n_split * 32, 256), 256, 0, s, P->split, P->n_split, carry, y);
+    if (P->n_split) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)div_up((int64_t)P->n_split * 32, 256));
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute at = {};
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        (void)cudaStreamIsCapturing(s, &cap);   // (inside a graph capture -- the multi-GPU step -- a plain edge)
+        cfg.attrs = &at;
+        cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;
+        const int32_t *split = P->split;
+        const int n_split = P->n_split;
+        const double *cr = carry;
+        CSRK_CUDA(cudaLaunchKernelEx(&cfg, k_slab_fixup<MULTI>, split, n_split, cr, y));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return CSRK_OK;
 }
 
