@@ -34,6 +34,8 @@
 // Cost model: HBM bytes are the stream + x once + y; the L2->SM fabric carries the stream
 // plus G copies of x, which is why auto mode only picks this kernel when G*ncols*X is below 1.6 x the stream size.
 #include <type_traits>
+#include <algorithm>
+#include <utility>
 
 #include "expand.cuh"
 #include "radix.cuh"
@@ -656,6 +658,7 @@ struct SlArgs {
     const int32_t *rowmap;
     int nslab, S, P, NW, slab_bytes, ring, nst, nxb;
     int32_t ncols;
+    unsigned long long *dbg;   // CSRK_SLAB_TIMING=1: per consumer warp, globaltimer at the end of its walk / of its epilogue
 };
 
 // shared-memory accesses by 32-bit shared address (the ring offset arithmetic below is done on addresses)
@@ -1009,14 +1012,35 @@ k_spmv_slab(SlArgs a, const XT *__restrict__ x, YOut y, double *__restrict__ car
             lap++;
         }
     }
+    if (a.dbg && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.dbg[2 * bin] = t;
+    }
     // ---------------- results: rows straight to y, pieces of split rows to their carry slots
+    // (eight row ids per lane are fetched together: one load latency per 256 rows instead of one per 32 -- the
+    // dependent load -> store chain of the plain loop kept the last warps busy for 8 us after their walk)
     const int32_t *rm = a.rowmap + bin * a.P;
-    for (int i = lane; i < a.P; i += 32) {
-        const int32_t r = rm[i];
-        if (r >= 0)
-            store_y<MULTI>(y, r, lds_f64(acc_w + 8u * i), true);
-        else if (r <= -2)
-            carry[-(r + 2)] = lds_f64(acc_w + 8u * i);
+    for (int i0 = 0; i0 < a.P; i0 += 256) {
+        int32_t r[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = i0 + 32 * u + lane;
+            r[u] = i < a.P ? ld_stream_i32(rm + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = i0 + 32 * u + lane;
+            if (r[u] >= 0)
+                store_y<MULTI>(y, r[u], lds_f64(acc_w + 8u * i), true);
+            else if (r[u] <= -2)
+                carry[-(r[u] + 2)] = lds_f64(acc_w + 8u * i);
+        }
+    }
+    if (a.dbg && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.dbg[2 * bin + 1] = t;
     }
 }
 
@@ -1118,15 +1142,59 @@ int stream_run(csrk_matrix *h, StreamPlan *P, const void *d_x, const YOut &y, cu
     a.nst = P->nst;
     a.nxb = P->nxb;
     a.ncols = h->ncols;
+    a.dbg = nullptr;
+    static const bool timing = getenv("CSRK_SLAB_TIMING") != nullptr;
+    DevBuf dbg;
+    if (timing) {
+        CSRK_TRY(dbg.alloc_zero(sizeof(unsigned long long) * 2 * (size_t)P->G * P->NW, s));
+        a.dbg = dbg.as<unsigned long long>();
+    }
     // carry slots of the split rows: per call (concurrent calls on one handle must not share them)
     DevBuf carry;
     if (P->n_split)
         CSRK_TRY(carry.alloc(sizeof(double) * (size_t)P->Q, s));
+    int rc;
     switch (h->val_kind) {
-    case 4: return slab_launch_x<float>(P, a, d_x, y, carry.as<double>(), s, h->nrows);
-    case 8: return slab_launch_x<double>(P, a, d_x, y, carry.as<double>(), s, h->nrows);
-    default: return slab_launch_x<NoVal>(P, a, d_x, y, carry.as<double>(), s, h->nrows);
+    case 4: rc = slab_launch_x<float>(P, a, d_x, y, carry.as<double>(), s, h->nrows); break;
+    case 8: rc = slab_launch_x<double>(P, a, d_x, y, carry.as<double>(), s, h->nrows); break;
+    default: rc = slab_launch_x<NoVal>(P, a, d_x, y, carry.as<double>(), s, h->nrows); break;
     }
+    if (timing && rc == CSRK_OK) {   // diagnostic: how evenly do the warps finish?
+        std::vector<unsigned long long> t(2 * (size_t)P->G * P->NW);
+        CSRK_CUDA(cudaMemcpyAsync(t.data(), a.dbg, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CSRK_CUDA(cudaStreamSynchronize(s));
+        unsigned long long lo = ~0ull, hi = 0, hi2 = 0;
+        for (size_t i = 0; i < t.size(); i += 2) {
+            lo = std::min(lo, t[i]);
+            hi = std::max(hi, t[i]);
+            hi2 = std::max(hi2, t[i + 1]);
+        }
+        double sum = 0;
+        for (size_t i = 0; i < t.size(); i += 2)
+            sum += (double)(t[i] - lo);
+        const double mean = sum / (t.size() / 2);
+        unsigned long long cmin = ~0ull, cmax = 0;
+        std::vector<std::pair<unsigned long long, int>> ce;
+        for (int g = 0; g < P->G; g++) {
+            unsigned long long c = 0;
+            for (int w = 0; w < P->NW; w++)
+                c = std::max(c, t[2 * ((size_t)g * P->NW + w)]);
+            cmin = std::min(cmin, c), cmax = std::max(cmax, c);
+            ce.push_back({c, g});
+        }
+        std::sort(ce.begin(), ce.end());
+        fprintf(stderr, "[csrk] slab CTAs by end time (us after the first): median %.1f; last six:", (double)(ce[ce.size() / 2].first - cmin) / 1e3);
+        for (size_t i = ce.size() >= 6 ? ce.size() - 6 : 0; i < ce.size(); i++)
+            fprintf(stderr, " #%d %.1f", ce[i].second, (double)(ce[i].first - cmin) / 1e3);
+        fprintf(stderr, "; first three:");
+        for (size_t i = 0; i < 3 && i < ce.size(); i++)
+            fprintf(stderr, " #%d", ce[i].second);
+        fprintf(stderr, "\n");
+        fprintf(stderr, "[csrk] slab warps: the first walk ends %.1f us before the mean, the last %.1f us after it; epilogues end "
+                        "%.1f us after the last walk; last warp of a CTA: %.1f us between the CTAs\n",
+                mean / 1e3, ((double)(hi - lo) - mean) / 1e3, (double)(hi2 - hi) / 1e3, (double)(cmax - cmin) / 1e3);
+    }
+    return rc;
 }
 
 void stream_info(const StreamPlan *P, int64_t *out /*[11]*/)
