@@ -1030,8 +1030,12 @@ __global__ void __launch_bounds__(256) k_col_expo(MatView B, int *__restrict__ e
 {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < B.nnz; k += (int64_t)gridDim.x * blockDim.x) {
         const double v = ld_val(B.vs, B.vk, k);
-        if (v != 0.0)
-            atomicMax(&eb[B.ci[k]], (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1022);
+        if (v != 0.0) {
+            const int e = (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1022;
+            int *p = &eb[B.ci[k]];
+            if (__ldcg(p) < e)   // (a plain read first: after a column's first few entries almost no atomic is left --
+                atomicMax(p, e);  //  the popular columns of rating data otherwise serialise 10^5 atomics on one address)
+        }
     }
 }
 // bit patterns of the smallest non-zero and the largest finite |v| (mm[0], mm[1]): a narrow range lets the

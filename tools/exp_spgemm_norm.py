@@ -9,6 +9,8 @@ K = get_kernel("cuda")
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 kinds = sys.argv[3].split(",") if len(sys.argv) > 3 else ["raw", "center", "unit"]
+for kv in sys.argv[4:]:
+    k, v = kv.split("="); K.set_option(k, int(v)); print("option", k, v)
 R = synth.cfg3_ratings(scale)
 rh = K.to_handle(R)
 for kind in kinds:
