@@ -1566,7 +1566,8 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     // hands back (skewed beyond a pseudo-row's capacity) and everything else follow the bins below.
     EscState esc;
     const int64_t esc_opt = options().spgemm_esc.load();
-    if (esc_opt == 2 || (esc_opt == 1 && div_up((int64_t)n, DENSE_WIN) > DENSE_MAX_PASSES)) {
+    if ((esc_opt == 2 || (esc_opt == 1 && div_up((int64_t)n, DENSE_WIN) > DENSE_MAX_PASSES)) &&
+        P / 16 < (1ull << 30)) {   // (pseudo-row and work-item counts are 32-bit)
         CSRK_TRY(esc_symbolic(A, B, L + off[3], cnt[3] + cnt[4] + cnt[5], prod.as<int64_t>(), both_f32, row_nnz.as<int32_t>(),
                               esc, s));
         if (esc.active)
