@@ -80,7 +80,8 @@ int csrk_synchronize(void);
  *               overflows the owner-computes kernel redoes the heavy rows);
  * "spgemm_esc"  SpGEMM expand/sort/compress path: 0 off | 1 for wide results (more than four shared-memory column
  *               windows: ncols > 106 496) | 2 always; "esc_target" 16..4096 products per pseudo-row (row x column
- *               range) of that path; "esc_budget" > 0 caps the bytes of its expansion (default: half of the free
+ *               range) of that path; "esc_stride" 1 | 0: its count kernel takes the work items a prime stride apart;
+ *               "esc_budget" > 0 caps the bytes of its expansion (default: half of the free
  *               device memory; over budget the path declines and the per-row kernels run). */
 int csrk_set_option(const char *name, int64_t value);
 /* the library's own (non-blocking) stream, as a cudaStream_t */
