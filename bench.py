@@ -994,6 +994,13 @@ def bench_cfg4(args, env):
     ns = max(min(ns, nrows), 1)
     es = int(rp[ns].item())
     S = orc.Mat(ns, ncols, es, rp[:ns + 1].cpu().numpy(), ci[:es].cpu().numpy(), vs[:es].cpu().numpy())
+    # the leading rows of this block (about cfg4_tile_nnz entries): this rank's operand of the A*A^T tile below
+    tile = None
+    if args.cfg4_tile_nnz > 0:
+        mt = int(torch.searchsorted(rp, torch.tensor([int(args.cfg4_tile_nnz)], device=dev)).item())
+        mt = max(min(mt, nrows), 1)
+        et = int(rp[mt].item())
+        tile = (mt, et, rp[:mt + 1].clone(), ci[:et].clone(), vs[:et].clone())
     del rp, rpd, ci, vs
     torch.cuda.empty_cache()
     shell = type("Block", (), dict(nrows=nrows, ncols=ncols, nnz=nnz, rowptrs=np.array([0, nnz], np.int64)))()
@@ -1036,7 +1043,9 @@ def bench_cfg4(args, env):
     env["allok"](ok, "cfg4 SpMV " + ptxt)
     kname, _ = spmv_kernel_name(K, h)
     ds.close()
-    return {"workload": f"BASELINE configs[4]: row-partitioned SpMV, {ncols}x{ncols}, {nnz * world} nnz float32 over {world} GPUs "
+    aat = bench_cfg4_aat(args, env, tile, ncols, dev) if tile is not None else None
+    return {**({"aat": aat} if aat is not None else {}),
+            "workload": f"BASELINE configs[4]: row-partitioned SpMV, {ncols}x{ncols}, {nnz * world} nnz float32 over {world} GPUs "
                         f"({nrows} rows, {nnz} nnz per GPU), generated on the devices",
             "value": round(total / ms / 1e6, 1), "unit": "GB/s", "ms_per_step": round(ms, 5), "kernel_ms": round(ms_k, 5),
             "kernel": kname, "per_gpu_frac_of_peak": round(local_bytes / ms_k / 1e6 / env["peak"], 4),
@@ -1044,6 +1053,107 @@ def bench_cfg4(args, env):
             "parallelism": ("NVLS multicast of x + in-kernel multicast gather of y" + (", one CUDA graph per step" if graphed else ""))
             if ds.nvls is not None else "NCCL broadcast(x) + all-gather(y)",
             "parity": "every rank: " + ptxt}
+
+
+def bench_cfg4_aat(args, env, tile, ncols, dev):
+    """configs[4], second half: A*A^T on the 2B-nnz matrix.  The full product has ~2e11 entries (2.4 TB), so every rank
+    forms ONE tile of it: (its leading rows) x (the leading rows of the NEXT rank's block)^T -- the operand block travels
+    over NCCL (ring exchange of the three CSR arrays), mult_abt transposes it on the device and the wide-result path
+    (expand / sort / compress) multiplies.  Parity without a host copy of 2e8-entry operands: (i) every row sum of the
+    tile equals (A_r * colsum(A_s))_i -- two SpMVs through the library and one index_add; (ii) the first rows of the tile,
+    restricted to the first columns, against the oracle product of the corresponding sub-blocks, bit for bit in
+    structure."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as orc
+    K, rank, world = env["K"], env["rank"], env["world"]
+    allmax, allsum = env["allmax"], env["allsum"]
+    mt, et, rp_a, ci_a, vs_a = tile
+    st = torch.cuda.current_stream().cuda_stream
+    # ---- ring exchange: my tile operand goes to rank-1, rank+1's comes to me
+    t0 = time.perf_counter()
+    hdr = torch.tensor([mt, et], dtype=torch.int64, device=dev)
+    hdrs = [torch.zeros_like(hdr) for _ in range(world)]
+    dist.all_gather(hdrs, hdr)
+    src, dst = (rank + 1) % world, (rank - 1) % world
+    mb, eb = (int(v) for v in hdrs[src].tolist())
+    rp_b = torch.empty(mb + 1, dtype=torch.int64, device=dev)
+    ci_b = torch.empty(eb, dtype=torch.int32, device=dev)
+    vs_b = torch.empty(eb, dtype=torch.float32, device=dev)
+    ops = []
+    for snd, rcv in ((rp_a, rp_b), (ci_a, ci_b), (vs_a, vs_b)):
+        ops.append(dist.P2POp(dist.isend, snd, dst))
+        ops.append(dist.P2POp(dist.irecv, rcv, src))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    torch.cuda.synchronize()
+    t_x = allmax(time.perf_counter() - t0)
+    res, ok, err = None, True, ""
+    try:
+        rpa32, rpb32 = rp_a.to(torch.int32), rp_b.to(torch.int32)
+        ah = K.from_device_arrays(mt, ncols, et, rpa32.data_ptr(), 0, ci_a.data_ptr(), vs_a.data_ptr(), 4, st)
+        bh = K.from_device_arrays(mb, ncols, eb, rpb32.data_ptr(), 0, ci_b.data_ptr(), vs_b.data_ptr(), 4, st)
+        torch.cuda.synchronize()
+        K.release_handle(K.mult_abt(ah, bh))        # warm-up: sizes the memory pool
+        K.synchronize()
+        t0 = time.perf_counter()
+        ch = K.mult_abt(ah, bh)
+        t_mm = time.perf_counter() - t0
+        stt = K.spgemm_stats(ch)
+        # (i) row sums
+        colsum_b = torch.zeros(ncols, dtype=torch.float64, device=dev).index_add_(0, ci_b.long(), vs_b.double())
+        y_c = torch.empty(mt, dtype=torch.float64, device=dev)
+        y_a = torch.empty(mt, dtype=torch.float64, device=dev)
+        ones = torch.ones(mb, dtype=torch.float64, device=dev)
+        K.mult_vec_dev(ch, ones.data_ptr(), 8, y_c.data_ptr(), st)
+        K.mult_vec_dev(ah, colsum_b.data_ptr(), 8, y_a.data_ptr(), st)
+        torch.cuda.synchronize()
+        rel = float(((y_c - y_a).abs() / y_a.abs().clamp_min(1e-300)).max().item())
+        ok = ok and rel <= 1e-9
+        # (ii) a corner of the tile against the oracle
+        na = int(torch.searchsorted(rp_a, torch.tensor([20000], device=dev)).item())
+        na = max(min(na, mt), 1)
+        nb = max(min(200_000, mb), 1)
+        ea_, eb_ = int(rp_a[na].item()), int(rp_b[nb].item())
+        Ao = orc.Mat(na, ncols, ea_, rp_a[:na + 1].cpu().numpy(), ci_a[:ea_].cpu().numpy(), vs_a[:ea_].cpu().numpy())
+        Bo = orc.Mat(nb, ncols, eb_, rp_b[:nb + 1].cpu().numpy(), ci_b[:eb_].cpu().numpy(), vs_b[:eb_].cpu().numpy())
+        ref = orc.canonical(orc.mult_abt(Ao, Bo))
+        sh = K.subset_rows(ch, 0, na)
+        G = K.from_handle(sh)
+        K.release_handle(sh)
+        grp = np.asarray(G.rowptrs, np.int64)
+        keep = G.colinds < nb
+        rows = np.repeat(np.arange(na), np.diff(grp))
+        cnt = np.bincount(rows[keep], minlength=na)
+        same = (np.array_equal(cnt, np.diff(np.asarray(ref.rowptrs, np.int64))) and np.array_equal(G.colinds[keep], ref.colinds))
+        worst = float((np.abs(G.values[keep] - ref.values) / np.maximum(np.abs(ref.values), 1e-300)).max(initial=0.0)) if same else float("inf")
+        ok = ok and same and worst <= RTOL_F8
+        res = (int(stt["out_nnz"]), int(stt["products"]), t_mm, rel, na, int(ref.nnz), worst)
+        for hh in (ch, ah, bh):
+            K.release_handle(hh)
+    except Exception as e:      # (collectives below stay matched: a failing rank reports, nobody hangs)
+        ok, err = False, f"{type(e).__name__}: {e}"
+    n_ok = int(allsum(1.0 if ok and res is not None else 0.0))
+    if n_ok != world:
+        errs = err or ("parity" if res is not None else "")
+        if errs:
+            log(f"[rank {rank}] cfg4 A*A^T tile: {errs} {res}")
+        return {"error": f"{world - n_ok} of {world} ranks failed", "detail": errs[:300] if rank == 0 else ""}
+    Z, P, t_mm, rel, na, zref, worst = res
+    t_all = allmax(t_mm)
+    Zs, Ps = int(allsum(float(Z))), int(allsum(float(P)))
+    rel, worst = allmax(rel), allmax(worst)
+    return {"workload": f"BASELINE configs[4]: A*A^T on the {ncols}x{ncols} matrix, one tile per GPU: (leading {mt} rows, {et} nnz of "
+                        f"rank r's block) x (leading rows of rank r+1's block)^T, float32 operands, float64 result",
+            "tiles": world, "out_nnz": Zs, "products": Ps, "ms": round(t_all * 1e3, 2),
+            "value": round(Zs / t_all, 1), "unit": "nnz/s", "products_per_s": round(Ps / t_all, 1),
+            "exchange_ms": round(t_x * 1e3, 2),
+            "exchange": "ring exchange of the operand blocks over NCCL (batch_isend_irecv of rowptrs, colinds, values)",
+            "note": "the full product (~(nnz/ncols)^2 * ncols entries = 2e11, 2.4 TB) cannot exist; a tile is what a rank would "
+                    "form at a time.  mult_abt = device transpose of the received block + the expand/sort/compress SpGEMM path",
+            "parity": f"every rank: all {mt} row sums of its tile equal (A_r * colsum(A_s)) within {rel:.1e} (bound 1e-09); rows "
+                      f"0..{na} x columns 0..200000 of the tile against the oracle product of those sub-blocks ({zref} entries on "
+                      f"rank 0): structure bit-exact, values max rel err {worst:.2e} (bound {RTOL_F8:g})"}
 
 
 # ---------------------------------------------------------------- reference
@@ -1118,6 +1228,8 @@ def main():
     ap.add_argument("--cfg3-scale", type=float, default=1.0, help="N=1: scale of configs[3] (transpose + mult_ab), 0 = skip")
     ap.add_argument("--cfg3-products", type=float, default=4e9, help="products of the configs[3] mult_ab row block")
     ap.add_argument("--cfg4-nnz", type=float, default=2e9, help="N>1: total nnz of the configs[4] SpMV, 0 = skip")
+    ap.add_argument("--cfg4-tile-nnz", type=float, default=2.5e8,
+                    help="N>1: entries of each operand of the configs[4] A*A^T tile (leading rows of a rank's block), 0 = skip")
     ap.add_argument("--chunks", type=int, default=1, help="N>1: row chunks whose all-gathers overlap the next chunk's SpMV")
     ap.add_argument("--nvls", choices=["auto", "on", "off"], default="auto",
                     help="N>1: NVLink-multicast broadcast + in-kernel multicast gather (default when the box supports it)")

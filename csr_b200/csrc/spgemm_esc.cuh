@@ -46,14 +46,26 @@ struct EscState {
 };
 
 // ranges and work items per row
+// A row with several times more products than the result has columns comes out nearly dense: expanding it would
+// write dozens of products per output entry and its pseudo-rows would be a handful of columns hit hundreds of
+// times.  Such rows are handed back at once (bad = 1): the dense accumulators of spgemm.cu are made for them.
+constexpr int ESC_DENSE_FACTOR = 4;
+
 __global__ void __launch_bounds__(256) k_esc_rows(MatView A, const int32_t *__restrict__ rows, int n, const int64_t *__restrict__ prod,
-                                                   int64_t target, int *__restrict__ nrange, int *__restrict__ nitem)
+                                                   int64_t target, int64_t ncols_out, int *__restrict__ nrange,
+                                                   int *__restrict__ nitem, int *__restrict__ bad)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
     const int32_t row = rows[i];
     const int64_t len = ld_rp(A.rp, A.rp64, (int64_t)row + 1) - ld_rp(A.rp, A.rp64, row);
+    if (prod[row] > ESC_DENSE_FACTOR * ncols_out) {
+        nrange[i] = 0;
+        nitem[i] = 0;
+        bad[i] = 1;
+        return;
+    }
     nrange[i] = (int)((prod[row] + target - 1) / target);
     nitem[i] = (int)((len + ESC_ITEM - 1) / ESC_ITEM);
 }
@@ -723,7 +735,9 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     CSRK_TRY(nitem.alloc(sizeof(int) * (size_t)n, s));
     CSRK_TRY(item_off.alloc(sizeof(int) * ((size_t)n + 1), s));
     CSRK_TRY(st.pbase.alloc(sizeof(int) * ((size_t)n + 1), s));
-    CSRK_LAUNCH(k_esc_rows, (unsigned)div_up(n, 256), 256, 0, s, A, rows, n, prod, target, nrange.as<int>(), nitem.as<int>());
+    CSRK_TRY(st.bad.alloc_zero(sizeof(int) * (size_t)n, s));
+    CSRK_LAUNCH(k_esc_rows, (unsigned)div_up(n, 256), 256, 0, s, A, rows, n, prod, target, (int64_t)B.ncols, nrange.as<int>(),
+                nitem.as<int>(), st.bad.as<int>());
     CSRK_TRY((exclusive_scan<int>(ArrayLoader<int>{nrange.as<int>()}, (int64_t)n, st.pbase.as<int>(), s)));
     CSRK_TRY((exclusive_scan<int>(ArrayLoader<int>{nitem.as<int>()}, (int64_t)n, item_off.as<int>(), s)));
     int tot[2] = {0, 0};
@@ -738,7 +752,6 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     CSRK_TRY(pcount.alloc_zero(sizeof(unsigned) * (size_t)np, s));
     CSRK_TRY(st.prow.alloc(sizeof(int32_t) * (size_t)np, s));
     CSRK_TRY(st.poff.alloc(sizeof(int64_t) * ((size_t)np + 1), s));
-    CSRK_TRY(st.bad.alloc_zero(sizeof(int) * (size_t)n, s));
     CSRK_TRY(st.old_list.alloc(sizeof(int32_t) * (size_t)n, s));
     CSRK_TRY(n_old_d.alloc_zero(sizeof(int), s));
     CSRK_LAUNCH(k_esc_prow, (unsigned)div_up((int64_t)n * 32, 256), 256, 0, s, st.pbase.as<int>(), n, st.prow.as<int32_t>());

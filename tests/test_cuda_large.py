@@ -255,6 +255,23 @@ def test_spgemm_esc_hands_back_skewed_rows(kernel):
     assert (P > 8192).any() and ((P > 1024) & (P <= 8192)).any()
 
 
+def test_spgemm_esc_hands_back_dense_rows(kernel):
+    """A row with more than four times as many products as the result has columns (here: full rows of A) comes out
+    nearly dense; the expand/sort/compress path hands it to the dense accumulators and keeps the others."""
+    A = synth.powerlaw_csr(300, 2000, 30000, seed=72, dtype="f8", alpha=1.0)
+    lens = np.diff(A.rowptrs).astype(np.int64)
+    lens[7] = lens[200] = 2000                       # two full rows: P = nnz(B) = 600 000 > 4 * 120 000
+    rp = np.zeros(301, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    rng = np.random.default_rng(73)
+    cols = synth.stratified_columns(lens, 2000, rng)
+    A = CSR(300, 2000, int(rp[-1]), rp, cols, rng.normal(size=int(rp[-1])))
+    B = synth.powerlaw_csr(2000, 120_000, 600_000, seed=74, dtype="f8", alpha=0.6)
+    got, st = _check_mm(kernel, A, B, False, 1e-10)
+    nz = np.diff(got.rowptrs)
+    assert nz[7] > 100_000 and nz[200] > 100_000
+
+
 def test_spgemm_esc_declines_over_budget(kernel):
     A = synth.powerlaw_csr(300, 2000, 40000, seed=53, dtype="f8", alpha=1.2)
     B = synth.powerlaw_csr(2000, 2_000_000, 300000, seed=54, dtype="f8", alpha=0.5)
