@@ -62,14 +62,33 @@ __device__ __forceinline__ double product(double av, double bv, int both_f32)
 }
 
 // ------------------------------------------------------------ step 0: products
+// One warp per row; rows longer than ROWP_LONG entries (the 10^7-entry rows of configs[4]: one warp needed 171 ms for
+// the longest) are cut into pieces of ROWP_LONG entries that k_row_products_long's CTAs sum and add atomically.
+constexpr int ROWP_LONG = 1 << 16;
+
 __global__ void __launch_bounds__(256) k_row_products(MatView A, MatView B, int64_t *__restrict__ prod,
-                                                      unsigned long long *__restrict__ total)
+                                                      unsigned long long *__restrict__ total, int64_t *__restrict__ long_items,
+                                                      int max_items)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t p = 0;
     if (row < A.nrows) {
         const int64_t s = ld_rp(A.rp, A.rp64, row), e = ld_rp(A.rp, A.rp64, row + 1);
+        if (e - s > ROWP_LONG) {
+            const int n = (int)((e - s + ROWP_LONG - 1) / ROWP_LONG);
+            if (lane == 0) {
+                prod[row] = 0;
+                atomicMax(total + 2, (unsigned long long)(e - s));
+            }
+            int base = 0;
+            if (lane == 0)
+                base = (int)atomicAdd(total + 3, (unsigned long long)n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int c = lane; c < n && base + c < max_items; c += 32)
+                long_items[base + c] = (row << 20) | c;   // (fewer than 2^20 pieces per row: rows have < 2^31 entries)
+            return;
+        }
         for (int64_t jj = s + lane; jj < e; jj += 32) {
             const int32_t j = A.ci[jj];
             p += ld_rp(B.rp, B.rp64, (int64_t)j + 1) - ld_rp(B.rp, B.rp64, j);
@@ -84,6 +103,47 @@ __global__ void __launch_bounds__(256) k_row_products(MatView A, MatView B, int6
             }
         }
     }
+}
+
+// the pieces of the long rows: persistent CTAs over the item list (its length is still on the device)
+__global__ void __launch_bounds__(256) k_row_products_long(MatView A, MatView B, int64_t *__restrict__ prod,
+                                                           unsigned long long *__restrict__ total,
+                                                           const int64_t *__restrict__ long_items, int max_items)
+{
+    __shared__ long long s_sum[8];
+    const int n = (int)min((unsigned long long)max_items, total[3]);
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const int64_t row = long_items[it] >> 20, c = long_items[it] & ((1 << 20) - 1);
+        const int64_t s = ld_rp(A.rp, A.rp64, row) + c * ROWP_LONG, e = min(ld_rp(A.rp, A.rp64, row + 1), s + ROWP_LONG);
+        long long p = 0;
+        for (int64_t jj = s + threadIdx.x; jj < e; jj += 256) {
+            const int32_t j = A.ci[jj];
+            p += ld_rp(B.rp, B.rp64, (int64_t)j + 1) - ld_rp(B.rp, B.rp64, j);
+        }
+        p = warp_sum(p);
+        if ((threadIdx.x & 31) == 0)
+            s_sum[threadIdx.x >> 5] = p;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long t = 0;
+            for (int w = 0; w < 8; w++)
+                t += s_sum[w];
+            if (t) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(prod) + row, (unsigned long long)t);
+                atomicAdd(total, (unsigned long long)t);
+            }
+        }
+        __syncthreads();
+    }
+}
+// the heaviest row may be one of the long ones
+__global__ void __launch_bounds__(256) k_row_products_max(const int64_t *__restrict__ prod, unsigned long long *__restrict__ total,
+                                                          const int64_t *__restrict__ long_items, int max_items)
+{
+    const int n = (int)min((unsigned long long)max_items, total[3]);
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x)
+        if ((long_items[it] & ((1 << 20) - 1)) == 0)
+            atomicMax(total + 1, (unsigned long long)prod[long_items[it] >> 20]);
 }
 
 // ------------------------------------------------------------------- binning
@@ -1534,9 +1594,18 @@ int spgemm_run(csrk_matrix *a, csrk_matrix *b, csrk_matrix **c, cudaStream_t s)
     // ---- step 0: products per row
     DevBuf prod, total;
     CSRK_TRY(prod.alloc(sizeof(int64_t) * (size_t)m, s));
-    CSRK_TRY(total.alloc_zero(sizeof(unsigned long long) * 3, s));
+    CSRK_TRY(total.alloc_zero(sizeof(unsigned long long) * 4, s));
+    DevBuf long_items;   // pieces of rows longer than ROWP_LONG entries: at most nnz / ROWP_LONG + one per such row
+    const int max_items = (int)std::min<int64_t>(a->nnz / ROWP_LONG * 2 + 1, INT32_MAX);
+    CSRK_TRY(long_items.alloc(sizeof(int64_t) * (size_t)max_items, s));
     CSRK_LAUNCH(k_row_products, (unsigned)div_up((int64_t)m * 32, 256), 256, 0, s, A, B, prod.as<int64_t>(),
-                total.as<unsigned long long>());
+                total.as<unsigned long long>(), long_items.as<int64_t>(), max_items);
+    if (a->nnz > ROWP_LONG) {
+        CSRK_LAUNCH(k_row_products_long, (unsigned)std::min(max_items, sms * 8), 256, 0, s, A, B, prod.as<int64_t>(),
+                    total.as<unsigned long long>(), long_items.as<int64_t>(), max_items);
+        CSRK_LAUNCH(k_row_products_max, (unsigned)std::min((int)div_up(max_items, 256), sms), 256, 0, s, prod.as<int64_t>(),
+                    total.as<unsigned long long>(), long_items.as<int64_t>(), max_items);
+    }
     unsigned long long PM[3] = {0, 0, 0};  // total products, products of the heaviest row, longest row (landed by bin_rows' sync)
     CSRK_CUDA(cudaMemcpyAsync(PM, total.p, sizeof PM, cudaMemcpyDeviceToHost, s));
 

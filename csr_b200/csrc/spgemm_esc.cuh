@@ -46,10 +46,12 @@ struct EscState {
 };
 
 // ranges and work items per row
-// A row with several times more products than the result has columns comes out nearly dense: expanding it would
-// write dozens of products per output entry and its pseudo-rows would be a handful of columns hit hundreds of
-// times.  Such rows are handed back at once (bad = 1): the dense accumulators of spgemm.cu are made for them.
-constexpr int ESC_DENSE_FACTOR = 4;
+// A row with hundreds of times more products than the result has columns is dense many times over: expanding it
+// would write hundreds of products per output entry.  Such rows are handed back at once (bad = 1) to the dense
+// accumulators of spgemm.cu.  (A factor of 4 was tried at configs[4] -- rows of 10^7 entries, up to 100 products per
+// output entry -- and lost: the global-scratch accumulator works one row per CTA, 1.5 s for a few dozen rows, while
+// their pseudo-rows -- some twenty columns hit 1536 times -- cost the hash kernel 60 ms in all.)
+constexpr int ESC_DENSE_FACTOR = 256;
 
 __global__ void __launch_bounds__(256) k_esc_rows(MatView A, const int32_t *__restrict__ rows, int n, const int64_t *__restrict__ prod,
                                                    int64_t target, int64_t ncols_out, int *__restrict__ nrange,
@@ -232,13 +234,24 @@ k_esc_count(MatView A, MatView B, const int32_t *__restrict__ rows, int n, const
         });
 }
 
-// pseudo-rows above the capacity: their row goes back to the caller
+// Pseudo-rows above the capacity.  If the row's column ranges are at most ESC_CAP columns wide, a pseudo-row has at
+// most ESC_CAP DISTINCT columns however many products pile up on them (A*A^T on power-law data: a popular column
+// collects a product from almost every entry of a heavy row): the hash kernel takes it as it is (fail = 1).
+// Otherwise the row goes back to the caller.
 __global__ void __launch_bounds__(256) k_esc_check(const unsigned *__restrict__ pcount, const int32_t *__restrict__ prow, int64_t np,
-                                                    int *__restrict__ bad)
+                                                    const int *__restrict__ pbase, int64_t ncols_out, int *__restrict__ bad,
+                                                    int *__restrict__ fail, int *__restrict__ any_fail)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < np && pcount[p] > (unsigned)ESC_CAP)
-        bad[prow[p]] = 1;
+    if (p < np && pcount[p] > (unsigned)ESC_CAP) {
+        const int i = prow[p];
+        const int64_t R = pbase[i + 1] - pbase[i];
+        if (ncols_out / R + 2 <= ESC_CAP) {
+            fail[p] = 1;
+            *any_fail = 1;
+        } else
+            bad[i] = 1;
+    }
 }
 __global__ void __launch_bounds__(256) k_esc_mask(unsigned *__restrict__ pcount, const int32_t *__restrict__ prow, int64_t np,
                                                    const int *__restrict__ bad)
@@ -540,7 +553,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_esc_sortmerge(const int32_t *
 // The general kernel for a pseudo-row of at most SLOTS/2 products: k_num_cta's hash accumulation + distribution
 // sort (spgemm.cu), reading the expansion instead of walking A and B, writing back into the segment.  Persistent
 // CTAs over the list; only pseudo-rows flagged by k_esc_sortmerge are taken.
-template <int SLOTS, int THREADS, int NBUCK>
+// AGG: the pseudo-rows of k_esc_check -- far more products than columns, millions on the most popular column: the
+// lanes of a warp that hold the same column add their values up first (match_any + 32 shuffles) and one of them
+// updates the table, so that a hot slot sees one CAS loop per warp and step instead of up to 32.
+template <int SLOTS, int THREADS, int NBUCK, bool AGG = false>
 __global__ void __launch_bounds__(THREADS) k_esc_reduce(const int32_t *__restrict__ plist, int nbin, const int64_t *__restrict__ poff,
                                                         int32_t *ecol, double *eval, int32_t *__restrict__ pnnz,
                                                         const int *__restrict__ fail, const int *__restrict__ any_fail)
@@ -578,9 +594,25 @@ __global__ void __launch_bounds__(THREADS) k_esc_reduce(const int32_t *__restric
         int32_t *oc = ecol + off;
         double *ov = eval + off;
         int kmin = INT32_MAX, kmax = -1, count = 0;
-        for (int i = tid; i < n; i += THREADS) {
-            const int32_t k = oc[i];
-            const double v = ov[i];
+        for (int i0 = 0; i0 < n; i0 += THREADS) {   // (uniform trip count: the AGG variant votes)
+            const int i = i0 + tid;
+            bool act = i < n;
+            int32_t k = act ? oc[i] : -1 - lane;     // (idle lanes: distinct negative keys, they match nobody)
+            double v = act ? ov[i] : 0.0;
+            if (AGG) {
+                const unsigned m = __match_any_sync(0xffffffffu, k);
+                double acc = 0.0;
+#pragma unroll 8
+                for (int l = 0; l < 32; l++) {
+                    const double vl = __shfl_sync(0xffffffffu, v, l);
+                    if ((m >> l) & 1u)
+                        acc += vl;                   // the group's values in lane order
+                }
+                act = act && lane == __ffs((int)m) - 1;
+                v = acc;
+            }
+            if (!act)
+                continue;
             kmin = min(kmin, k);
             kmax = max(kmax, k);
             unsigned h = hash_col(k, SLOTS - 1);
@@ -765,7 +797,11 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     CSRK_LAUNCH(k_esc_count, (unsigned)nitems, ESC_WALK_THREADS, 0, s, A, B, rows, n, item_off.as<int>(), st.pbase.as<int>(),
                 pcount.as<unsigned>(), stride);
     const unsigned pgrid = (unsigned)div_up(np, 256);
-    CSRK_LAUNCH(k_esc_check, pgrid, 256, 0, s, pcount.as<unsigned>(), st.prow.as<int32_t>(), np, st.bad.as<int>());
+    DevBuf fail;   // pseudo-rows for the hash kernel (set here for the oversized ones, later by the sort/merge kernels)
+    CSRK_TRY(fail.alloc_zero(sizeof(int) * ((size_t)np + 1), s));
+    int *fl = fail.as<int>(), *af = fl + np;
+    CSRK_LAUNCH(k_esc_check, pgrid, 256, 0, s, pcount.as<unsigned>(), st.prow.as<int32_t>(), np, st.pbase.as<int>(),
+                (int64_t)B.ncols, st.bad.as<int>(), fl, af);
     CSRK_LAUNCH(k_esc_mask, pgrid, 256, 0, s, pcount.as<unsigned>(), st.prow.as<int32_t>(), np, st.bad.as<int>());
     CSRK_LAUNCH(k_esc_badlist, (unsigned)div_up(n, 256), 256, 0, s, rows, n, st.bad.as<int>(), st.old_list.as<int32_t>(),
                 n_old_d.as<int>());
@@ -819,9 +855,6 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
     int32_t *pz = st.pnnz.as<int32_t>();
     if (cnt[1])
         CSRK_LAUNCH((k_esc_reduce_warp<128>), (unsigned)div_up(cnt[1], 8), 256, 0, s, PL + off[1], cnt[1], po, ec, ev, pz);
-    DevBuf fail;
-    CSRK_TRY(fail.alloc_zero(sizeof(int) * ((size_t)np + 1), s));
-    int *fl = fail.as<int>(), *af = fl + np;
     const int sms = ctx().sm_count;
     // bucket sort + merge, then the hash kernel for what it flagged (usually nothing: its CTAs only read the flags)
     if (cnt[2]) {
@@ -844,6 +877,11 @@ static int esc_symbolic(const MatView &A, const MatView &B, const int32_t *rows,
         auto h = k_esc_reduce<16384, 512, 4096>;
         CSRK_TRY(optin_smem(h, 16384 * 12 + 4096 * 4));
         CSRK_LAUNCH(h, (unsigned)std::min(cnt[4], sms), 512, 16384 * 12 + 4096 * 4, s, PL + off[4], cnt[4], po, ec, ev, pz, fl, af);
+    }
+    if (cnt[5]) {   // more products than ESC_CAP on at most ESC_CAP columns (k_esc_check): straight to the hash kernel
+        auto h = k_esc_reduce<16384, 512, 4096, true>;
+        CSRK_TRY(optin_smem(h, 16384 * 12 + 4096 * 4));
+        CSRK_LAUNCH(h, (unsigned)std::min(cnt[5], sms), 512, 16384 * 12 + 4096 * 4, s, PL + off[5], cnt[5], po, ec, ev, pz, fl, af);
     }
     CSRK_TRY(st.pg.alloc(sizeof(int64_t) * ((size_t)np + 1), s));
     CSRK_TRY((exclusive_scan<int64_t>(ArrayLoader<int32_t>{pz}, np, st.pg.as<int64_t>(), s)));

@@ -256,20 +256,54 @@ def test_spgemm_esc_hands_back_skewed_rows(kernel):
 
 
 def test_spgemm_esc_hands_back_dense_rows(kernel):
-    """A row with more than four times as many products as the result has columns (here: full rows of A) comes out
-    nearly dense; the expand/sort/compress path hands it to the dense accumulators and keeps the others."""
+    """A row with more than 256 times as many products as the result has columns (here: full rows of A against a 15 %
+    dense B) is handed to the dense accumulators at once; the other rows stay on the forced expand/sort/compress path."""
     A = synth.powerlaw_csr(300, 2000, 30000, seed=72, dtype="f8", alpha=1.0)
     lens = np.diff(A.rowptrs).astype(np.int64)
-    lens[7] = lens[200] = 2000                       # two full rows: P = nnz(B) = 600 000 > 4 * 120 000
+    lens[7] = lens[200] = 2000                       # two full rows: P = nnz(B) = 600 000 > 256 * 2000
     rp = np.zeros(301, np.int64)
     np.cumsum(lens, out=rp[1:])
     rng = np.random.default_rng(73)
     cols = synth.stratified_columns(lens, 2000, rng)
     A = CSR(300, 2000, int(rp[-1]), rp, cols, rng.normal(size=int(rp[-1])))
-    B = synth.powerlaw_csr(2000, 120_000, 600_000, seed=74, dtype="f8", alpha=0.6)
-    got, st = _check_mm(kernel, A, B, False, 1e-10)
+    B = synth.powerlaw_csr(2000, 2000, 600_000, seed=74, dtype="f8", alpha=0.3)
+    got, st = _with_options(kernel, {"spgemm_esc": 2}, lambda: _check_mm(kernel, A, B, False, 1e-10))
     nz = np.diff(got.rowptrs)
-    assert nz[7] > 100_000 and nz[200] > 100_000
+    assert nz[7] == 2000 or nz[7] > 1900
+
+
+def test_spgemm_esc_popular_column(kernel):
+    """Every row of B holds column 7: an output element collects a product from EVERY entry of A's row (15 000 in one
+    pseudo-row, beyond the 8192 the sort/merge kernels take); the ranges are narrow, so the hash kernel with warp
+    pre-aggregation takes such pseudo-rows (k_esc_check, k_esc_reduce<..., AGG>)."""
+    rng = np.random.default_rng(77)
+    lens = np.full(50, 40, np.int64)
+    lens[5], lens[31] = 15000, 9000
+    rp = np.zeros(51, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    A = CSR(50, 20000, int(rp[-1]), rp, synth.stratified_columns(lens, 20000, rng), rng.normal(size=int(rp[-1])))
+    bl = np.full(20000, 4, np.int64)
+    brp = np.zeros(20001, np.int64)
+    np.cumsum(bl, out=brp[1:])
+    bc = np.sort(np.concatenate([np.full((20000, 1), 7), rng.integers(8, 200_000, (20000, 3))], axis=1), axis=1).astype(np.int32)
+    B = CSR(20000, 200_000, 80000, brp, bc.reshape(-1), rng.normal(size=80000))
+    for target in (16, 1536):
+        _with_options(kernel, {"spgemm_esc": 2, "esc_target": target}, lambda: _check_mm(kernel, A, B, False, 1e-10))
+
+
+def test_spgemm_long_rows_of_a(kernel):
+    "rows of A beyond 65 536 entries: their product counts are summed piecewise (k_row_products_long)"
+    lens = np.full(40, 50, np.int64)
+    lens[3], lens[21] = 150_000, 70_001
+    rp = np.zeros(41, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    rng = np.random.default_rng(75)
+    cols = synth.stratified_columns(lens, 200_000, rng)
+    A = CSR(40, 200_000, int(rp[-1]), rp, cols, rng.normal(size=int(rp[-1])))
+    B = synth.powerlaw_csr(200_000, 3000, 600_000, seed=76, dtype="f8", alpha=0.5)
+    got, st = _check_mm(kernel, A, B, False, 1e-10)
+    lb = np.diff(B.rowptrs).astype(np.int64)
+    assert st["products"] == int(lb[A.colinds].sum())
 
 
 def test_spgemm_esc_declines_over_budget(kernel):
