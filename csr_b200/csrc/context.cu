@@ -622,10 +622,16 @@ static int copy_to_host(void *dst, const void *src, size_t bytes, cudaStream_t s
         }
     };
     std::thread th[OUT_THREADS];
-    for (int k = 0; k < OUT_THREADS; k++)
-        th[k] = std::thread(work, k);
-    for (int k = 0; k < OUT_THREADS; k++)
+    int started = 0;
+    try {
+        for (; started < OUT_THREADS; started++)
+            th[started] = std::thread(work, started);
+    } catch (...) {   // no more threads to be had: the chunks of the missing ones are copied here, afterwards
+    }
+    for (int k = 0; k < started; k++)
         th[k].join();
+    for (int k = started; k < OUT_THREADS; k++)
+        work(k);
     if (failed) {
         set_error("device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return CSRK_ECUDA;
