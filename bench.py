@@ -1064,7 +1064,7 @@ def bench_cfg4_aat(args, env, tile, ncols, dev):
     restricted to the first columns, against the oracle product of the corresponding sub-blocks, bit for bit in
     structure."""
     import torch
-    import torch.distributed as dist
+    from csr_b200.dist import ring_exchange
     from oracle import oracle as orc
     K, rank, world = env["K"], env["rank"], env["world"]
     allmax, allsum = env["allmax"], env["allsum"]
@@ -1072,20 +1072,8 @@ def bench_cfg4_aat(args, env, tile, ncols, dev):
     st = torch.cuda.current_stream().cuda_stream
     # ---- ring exchange: my tile operand goes to rank-1, rank+1's comes to me
     t0 = time.perf_counter()
-    hdr = torch.tensor([mt, et], dtype=torch.int64, device=dev)
-    hdrs = [torch.zeros_like(hdr) for _ in range(world)]
-    dist.all_gather(hdrs, hdr)
-    src, dst = (rank + 1) % world, (rank - 1) % world
-    mb, eb = (int(v) for v in hdrs[src].tolist())
-    rp_b = torch.empty(mb + 1, dtype=torch.int64, device=dev)
-    ci_b = torch.empty(eb, dtype=torch.int32, device=dev)
-    vs_b = torch.empty(eb, dtype=torch.float32, device=dev)
-    ops = []
-    for snd, rcv in ((rp_a, rp_b), (ci_a, ci_b), (vs_a, vs_b)):
-        ops.append(dist.P2POp(dist.isend, snd, dst))
-        ops.append(dist.P2POp(dist.irecv, rcv, src))
-    for w in dist.batch_isend_irecv(ops):
-        w.wait()
+    rp_b, ci_b, vs_b = ring_exchange([rp_a, ci_a, vs_a], shift=1)
+    mb, eb = int(rp_b.numel()) - 1, int(ci_b.numel())
     torch.cuda.synchronize()
     t_x = allmax(time.perf_counter() - t0)
     res, ok, err = None, True, ""
@@ -1148,7 +1136,7 @@ def bench_cfg4_aat(args, env, tile, ncols, dev):
             "tiles": world, "out_nnz": Zs, "products": Ps, "ms": round(t_all * 1e3, 2),
             "value": round(Zs / t_all, 1), "unit": "nnz/s", "products_per_s": round(Ps / t_all, 1),
             "exchange_ms": round(t_x * 1e3, 2),
-            "exchange": "ring exchange of the operand blocks over NCCL (batch_isend_irecv of rowptrs, colinds, values)",
+            "exchange": "csr_b200.dist.ring_exchange: the operand blocks move one rank along a ring over NCCL (batch_isend_irecv of rowptrs, colinds, values)",
             "note": "the full product (~(nnz/ncols)^2 * ncols entries = 2e11, 2.4 TB) cannot exist; a tile is what a rank would "
                     "form at a time.  mult_abt = device transpose of the received block + the expand/sort/compress SpGEMM path",
             "parity": f"every rank: all {mt} row sums of its tile equal (A_r * colsum(A_s)) within {rel:.1e} (bound 1e-09); rows "

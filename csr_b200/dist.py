@@ -386,6 +386,33 @@ def replicate_csr(mat, *, src: int = 0, group=None, device=None, csr_cls=None):
                    _cast=False)
 
 
+def ring_exchange(tensors, *, shift: int = 1, group=None):
+    """Every rank sends ``tensors`` -- a list of 1-D tensors, on the CPU (gloo) or on its GPU (NCCL) -- to rank
+    ``rank - shift`` and receives the list of rank ``rank + shift`` (lengths differ between ranks: they travel first,
+    in one all-gather).  This is how an operand BLOCK moves when a product is formed tile by tile: C = A A^T of a
+    row-partitioned A has the tiles A_r A_s^T, and a rank needs one foreign block at a time -- replicating A^T
+    (``replicate_csr``) is for operands that fit N times over; configs[4] (2e9 entries) does not."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1 or shift % world == 0:
+        return [t.clone() for t in tensors]
+    dev = tensors[0].device
+    hdr = torch.tensor([int(t.numel()) for t in tensors], dtype=torch.int64, device=dev)
+    hdrs = [torch.zeros_like(hdr) for _ in range(world)]
+    dist.all_gather(hdrs, hdr, group=group)
+    src, dst = (rank + shift) % world, (rank - shift) % world
+    recv = [torch.empty(int(n), dtype=t.dtype, device=dev) for n, t in zip(hdrs[src].tolist(), tensors)]
+    ops = []
+    for snd, rcv in zip(tensors, recv):
+        ops.append(dist.P2POp(dist.isend, snd.contiguous(), dst, group))
+        ops.append(dist.P2POp(dist.irecv, rcv, src, group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return recv
+
+
 def dist_multiply(a_local, b, *, transpose: bool = False, kernel=None, multiply=None):
     """This rank's block of C = A B (or A B^T): ``a_local`` is the rank's row block
     of A, ``b`` the replicated operand.  Returns the local block as a host CSR at

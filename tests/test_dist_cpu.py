@@ -75,7 +75,23 @@ def _worker(rank, world, port, q):
                  and np.array_equal(C.colinds, Cref.colinds) and np.array_equal(C.values, Cref.values))
         ok_rep = (Brep.nnz == Bfull.nnz and np.array_equal(Brep.colinds, Bfull.colinds)
                   and np.array_equal(Brep.values, Bfull.values) and Brep.rowptrs.dtype == Bfull.rowptrs.dtype)
-        q.put((rank, ok_spmv, ok_mm, ok_rep, counts))
+        # A A^T tile by tile: my row block times the NEXT rank's block, which arrives by a ring exchange
+        from csr_b200.dist import ring_exchange
+        got = ring_exchange([torch.from_numpy(np.asarray(mine.rowptrs, np.int64)), torch.from_numpy(mine.colinds.copy()),
+                             torch.from_numpy(mine.values.copy())])
+        nxt = (rank + 1) % world
+        other = A.subset_rows(cuts[nxt], cuts[nxt + 1])
+        ok_ring = (np.array_equal(got[0].numpy(), np.asarray(other.rowptrs, np.int64)) and
+                   np.array_equal(got[1].numpy(), other.colinds) and np.array_equal(got[2].numpy(), other.values))
+        nb = len(got[0]) - 1
+        tile = orc.canonical(orc.mult_abt(mine, CSR(nb, A.ncols, len(got[1]), got[0].numpy(), got[1].numpy(), got[2].numpy())))
+        full = orc.canonical(orc.mult_abt(A, A))
+        frp = np.asarray(full.rowptrs, np.int64)
+        rows = np.repeat(np.arange(A.nrows), np.diff(frp))
+        sel = (rows >= cuts[rank]) & (rows < cuts[rank + 1]) & (full.colinds >= cuts[nxt]) & (full.colinds < cuts[nxt + 1])
+        ok_ring = ok_ring and tile.nnz == int(sel.sum()) and np.array_equal(tile.colinds, full.colinds[sel] - cuts[nxt]) \
+            and np.array_equal(tile.values, full.values[sel])
+        q.put((rank, ok_spmv, ok_mm, ok_rep and ok_ring, counts))
     finally:
         dist.destroy_process_group()
 
@@ -109,7 +125,7 @@ def test_world2_gloo():
     for rank, ok_spmv, ok_mm, ok_rep, counts in res:
         assert ok_spmv, f"rank {rank}: distributed SpMV differs from the unsharded result"
         assert ok_mm, f"rank {rank}: assembled SpGEMM differs from the unsharded result"
-        assert ok_rep, f"rank {rank}: replicated B differs"
+        assert ok_rep, f"rank {rank}: replicated B differs, or the ring-exchanged block / its A A^T tile"
         assert sum(counts) == 700
 
 
