@@ -15,8 +15,14 @@
 //                       the dtype rule of csr/csr.py:90-93)
 //   3. numeric          rows binned by their exact nnz: shared-memory hash
 //                       accumulators (float64 values) sorted by column before
-//                       they are written, or a dense float64 accumulator + bitmap
-//                       whose sweep emits columns already in order.
+//                       they are written, or -- heavy rows -- a dense accumulator
+//                       over column windows in shared memory whose sweep emits the
+//                       columns in order: 64-bit fixed point on native atomics over
+//                       power-of-two equilibrated operands with an exact side list
+//                       (k_num_fixed), or float64 owner-computes without atomics
+//                       (k_num_owner).
+// Wide results (more columns than four windows) take the one-phase expand / sort /
+// compress path of spgemm_esc.cuh for every row above the small hash bins.
 // Products are formed in numba's promoted type (f4*f4 -> f4, else f8) and summed
 // in float64, like multiply.py:120.  Only the summation ORDER differs from the
 // reference (hence rtol instead of bit-exact values).
