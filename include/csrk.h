@@ -66,7 +66,10 @@ int csrk_synchronize(void);
  * "stream_slab_bytes" > 0 caps the x slab size, "stream_ctas" > 0 sets the number of CTAs (row groups),
  *               "stream_warps" 1..31 the consumer warps per CTA of the slab kernel, "stream_piece" 8..4096 the
  *               longest pseudo-row (longer rows are cut), "stream_ring_bytes" 4096 | 8192 the per-warp prefetch
- *               ring (tests, tuning);
+ *               ring, "stream_ring_chunks" 2 | 4 the bulk copies per ring, "stream_xbufs" 2 | 3 the x slabs resident
+ *               per CTA (tests, tuning);
+ * "sym_bytes"   1 | 0: SpGEMM symbolic pass of heavy rows marks columns with byte stores in shared memory when they
+ *               fit (else bitmap words with atomicOr);
  * "own_nw"      8 | 16 column ranges (warps) per CTA in the owner-computes SpGEMM numeric kernel;
  * "spmv_zero_copy_y" 1 | 0: csrk_spmv stores finished rows straight into y when y is pinned host memory;
  * "fix_threads" 512 | 768 | 1024 threads per CTA of that kernel (default 1024);

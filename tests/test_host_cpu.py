@@ -230,3 +230,14 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["metric"] == "spmv_hbm_gbs" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_every_option_is_documented_in_the_header():
+    "csrk_set_option's names (csrc/context.cu) all appear in the tunables comment of include/csrk.h"
+    import re
+    src = open(os.path.join(ROOT, "csr_b200", "csrc", "context.cu")).read()
+    hdr = open(os.path.join(ROOT, "include", "csrk.h")).read()
+    names = re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', src)
+    assert len(names) > 20
+    missing = [n for n in names if f'"{n}"' not in hdr]
+    assert not missing, missing
